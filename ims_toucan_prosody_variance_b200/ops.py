@@ -1,0 +1,147 @@
+"""Host-side wrappers over the C ABI: torch tensors in, raw pointers out.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic on the hot path happens in
+libtoucan_b200.so.  Activations are NCL (B, C, L) with per-utterance int32 lengths on device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_AA_SNAKEBETA, ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SWISH, ACT_TANH, F16, F32, OUT_NONE,
+                   OUT_RELU, OUT_TANH, PREC_F16, PREC_FP32_SIMT, PREC_TF32)
+
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "f16": PREC_F16, "tf32": PREC_TF32}
+
+LAUNCHES = 0  # kernels of ours enqueued since import (bench.py reports the per-step delta)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float16:
+        return F16
+    raise _lib.EngineError(f"unsupported activation dtype {t.dtype}")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.EngineError("toucan_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+class ConvLayer:
+    """One Conv1d / ConvTranspose1d / Linear with its weights packed for tb200_conv1d.
+
+    weight: torch layout, fp32 -- (C_out, C_in, K), or (C_in, C_out, 2u) when transposed_stride=u.
+    """
+
+    def __init__(self, weight, bias=None, dilation=1, padding=0, transposed_stride=0, precision="f16"):
+        lib = _lib.load()
+        _require_cuda(weight, bias)
+        weight = weight.detach().to(torch.float32).contiguous()
+        if weight.dim() == 2:
+            weight = weight.unsqueeze(-1)
+        self.up = int(transposed_stride)
+        if self.up:
+            self.c_in, self.c_out, self.k = weight.shape
+        else:
+            self.c_out, self.c_in, self.k = weight.shape
+        self.dilation, self.pad = int(dilation), int(padding)
+        self.precision = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        nbytes = lib.tb200_packed_weight_bytes(self.c_in, self.c_out, self.k, self.up, self.precision)
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        _lib.check(lib.tb200_pack_conv_weight(_ptr(weight), _ptr(self.packed), self.c_in, self.c_out, self.k, self.up,
+                                              self.precision, _lib.stream_ptr()), "tb200_pack_conv_weight")
+        self.bias = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+        self._p = _lib.Conv1dParams()
+
+    def out_len(self, length):
+        return length * self.up if self.up else length
+
+    def __call__(self, x, lengths, out, l_in_max=None, act=ACT_NONE, slope=0.0, alpha=None, beta=None, out_act=OUT_NONE,
+                 out_alpha=1.0, residual=None, res_beta=1.0, accumulate=False):
+        """x (B,C_in,L) -> out (B,C_out,L_out), both NCL with contiguous rows.  lengths: int32 (B) or None."""
+        global LAUNCHES
+        _require_cuda(x, out, residual, lengths)
+        if x.stride(2) != 1 or out.stride(2) != 1 or x.shape[1] != self.c_in or out.shape[1] != self.c_out:
+            raise _lib.EngineError(f"conv1d: bad tensor layout x={tuple(x.shape)} out={tuple(out.shape)} "
+                                   f"expected C_in={self.c_in} C_out={self.c_out}")
+        p = self._p
+        p.x, p.x_dtype, p.x_bs, p.x_ld = x.data_ptr(), _dtype_code(x), x.stride(0), x.stride(1)
+        p.len_in = lengths.data_ptr() if lengths is not None else None
+        p.B, p.C_in, p.L_in_max = x.shape[0], self.c_in, int(l_in_max if l_in_max is not None else x.shape[2])
+        p.C_out, p.K, p.dilation, p.pad, p.transposed_stride = self.c_out, self.k, self.dilation, self.pad, self.up
+        p.w_packed, p.bias, p.precision = self.packed.data_ptr(), (self.bias.data_ptr() if self.bias is not None else None), self.precision
+        p.act, p.act_slope = act, slope
+        p.act_alpha = alpha.data_ptr() if alpha is not None else None
+        p.act_beta = beta.data_ptr() if beta is not None else None
+        p.out_act, p.out_alpha = out_act, out_alpha
+        if residual is not None:
+            if residual.dtype != torch.float32 or residual.stride(2) != 1:
+                raise _lib.EngineError("conv1d: residual must be fp32 NCL")
+            p.residual, p.r_bs, p.r_ld = residual.data_ptr(), residual.stride(0), residual.stride(1)
+        else:
+            p.residual, p.r_bs, p.r_ld = None, 0, 0
+        p.res_beta, p.accumulate = res_beta, int(accumulate)
+        p.y, p.y_dtype, p.y_bs, p.y_ld = out.data_ptr(), _dtype_code(out), out.stride(0), out.stride(1)
+        if self.out_len(p.L_in_max) > out.shape[2]:
+            raise _lib.EngineError("conv1d: output buffer too short")
+        _lib.check(_lib.load().tb200_conv1d(ctypes.byref(p), _lib.stream_ptr()), "tb200_conv1d")
+        LAUNCHES += 1
+        return out
+
+
+def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1.0, duration_scale=1.0):
+    """text (B,T,62) fp32, text_len (B) int32, log_dur (B,T) fp32 or gold_dur (B,T) int64.
+    Returns durations (B,T) int64, inclusive prefix sums (B,T) int32, frames (B) int32."""
+    global LAUNCHES
+    _require_cuda(text, text_len, log_dur, gold_dur)
+    b, t, _ = text.shape
+    src = log_dur if log_dur is not None else gold_dur
+    src = src.contiguous()
+    text = text.contiguous()
+    dur = torch.empty((b, t), dtype=torch.int64, device=text.device)
+    cum = torch.empty((b, t), dtype=torch.int32, device=text.device)
+    frames = torch.empty((b,), dtype=torch.int32, device=text.device)
+    _lib.check(_lib.load().tb200_duration_finalize(
+        _ptr(src) if log_dur is not None else None, _ptr(src) if log_dur is None else None, _ptr(text), _ptr(text_len), b, t, t,
+        float(pause_scale), float(duration_scale), _ptr(dur), _ptr(cum), _ptr(frames), _lib.stream_ptr()),
+        "tb200_duration_finalize")
+    LAUNCHES += 1
+    return dur, cum, frames
+
+
+def variance_edit(curve, text, text_len, which, variance_scale=1.0):
+    """In-place pitch (which=0) / energy (which=1) edits + variance scaling on curve (B,T) fp32."""
+    global LAUNCHES
+    _require_cuda(curve, text, text_len)
+    b, t, _ = text.shape
+    if not curve.is_contiguous() or curve.shape != (b, t):
+        raise _lib.EngineError("variance_edit: curve must be contiguous (B,T)")
+    _lib.check(_lib.load().tb200_variance_edit(_ptr(curve), _ptr(text.contiguous()), _ptr(text_len), b, t, t, int(which),
+                                               float(variance_scale), _lib.stream_ptr()), "tb200_variance_edit")
+    LAUNCHES += 1
+    return curve
+
+
+def length_regulate(enc, cum, text_len, frames, f_max, pitch=None, energy=None, wp=None, bp=None, we=None, be=None,
+                    out=None, want_index=False):
+    """enc (B,C,T) NCL fp32 -> (B,C,F_max) NCL fp32 (only f < frames[b] written)."""
+    global LAUNCHES
+    _require_cuda(enc, cum, text_len, frames, pitch, energy)
+    b, c, _ = enc.shape
+    f_ld = (f_max + 3) // 4 * 4
+    if out is None:
+        out = torch.zeros((b, c, f_ld), dtype=torch.float32, device=enc.device)
+    f2p = torch.full((b, f_ld), -1, dtype=torch.int32, device=enc.device) if want_index else None
+    _lib.check(_lib.load().tb200_length_regulate(
+        _ptr(enc), enc.stride(0), enc.stride(1), _ptr(pitch), _ptr(energy), pitch.stride(0) if pitch is not None else 0,
+        _ptr(wp), _ptr(bp), _ptr(we), _ptr(be), _ptr(cum), cum.stride(0), _ptr(text_len), _ptr(frames), b, c, int(f_max),
+        _ptr(out), out.stride(0), out.stride(1), _ptr(f2p), f_ld, _lib.stream_ptr()), "tb200_length_regulate")
+    LAUNCHES += 1
+    return (out, f2p) if want_index else out

@@ -1,0 +1,218 @@
+"""Drop-in vocoder generators: HiFiGAN ("Avocodo") and BigVGAN on the B200 engine.
+
+Same constructor and forward signatures and the same state_dict layout as
+InferenceInterfaces/InferenceArchitectures/InferenceAvocodo.py:6-96 and InferenceBigVGAN.py:19-121 of
+the reference; `forward(c)` keeps the reference's batch-1 contract ((80,T) -> (T*384,)), and
+`forward_batch` is the additive batched entry ((B,80,T) + per-utterance lengths), whose result for
+each utterance equals a batch-1 call (zero / replicate padding at the utterance's own ends).
+
+Every convolution of the generator is one tb200_conv1d launch with its activation fused in the
+prologue (LeakyReLU, or BigVGAN's anti-aliased SnakeBeta) and bias / residual / the 1/3 multi-
+receptive-field mean fused in the epilogue.  The residual stream stays fp32 in HBM; the value between
+the two convs of a residual pair is stored as fp16 (it is only ever consumed as a tensor-core operand).
+"""
+import torch
+
+from . import layouts, ops
+from ._lib import ACT_AA_SNAKEBETA, ACT_LEAKY_RELU, ACT_NONE, OUT_NONE, OUT_TANH
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class _GeneratorBase(torch.nn.Module):
+    """Shared engine of the two generators; subclasses provide the key naming and activations."""
+
+    upsample_scales = (8, 6, 4, 2)
+
+    def _init_engine(self, precision):
+        self.precision = precision
+        self._packed = None
+        self._buffers_cache = {}
+
+    # -- to be provided by subclasses --------------------------------------------------------
+    def _names(self):
+        raise NotImplementedError
+
+    def _stage_channels(self, i):
+        return self.channels // 2 ** (i + 1)
+
+    # -- load-time packing -------------------------------------------------------------------
+    @torch.no_grad()
+    def remove_weight_norm(self):
+        """Reference: folds weight_g * v/||v|| into .weight (InferenceAvocodo.py:82-89,
+        InferenceBigVGAN.py:97-105).  Here: fold on the parameters' device and pack the tensor-core
+        operand images.  The weight_g / weight_v parameters stay as they are (state_dict unchanged)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise ops._lib.EngineError("toucan_b200 generators run on CUDA only: call .to('cuda') before "
+                                       "remove_weight_norm()/forward()")
+        sd = layouts.fold_weight_norm({k: v.detach() for k, v in self.state_dict().items()})
+        n = self._names()
+        prec = self.precision
+        pk = {}
+        pk["pre"] = ops.ConvLayer(sd[n["pre"] + ".weight"], sd[n["pre"] + ".bias"], padding=(self.kernel_size - 1) // 2,
+                                  precision=prec)
+        for i, (u, k) in enumerate(zip(self.upsample_scales, self.upsample_kernel_sizes)):
+            if k != 2 * u or u % 2:
+                raise ops._lib.EngineError("the engine supports upsampling layers with kernel == 2*stride, stride even")
+            pk[f"up{i}"] = ops.ConvLayer(sd[n["up"].format(i) + ".weight"], sd[n["up"].format(i) + ".bias"],
+                                         transposed_stride=u, precision=prec)
+            for j, kr in enumerate(self.resblock_kernel_sizes):
+                blk = i * len(self.resblock_kernel_sizes) + j
+                for m, d in enumerate(self.resblock_dilations[j]):
+                    c1, c2 = n["c1"].format(blk, m), n["c2"].format(blk, m)
+                    pk[f"b{blk}.c1.{m}"] = ops.ConvLayer(sd[c1 + ".weight"], sd[c1 + ".bias"], dilation=d,
+                                                         padding=(kr - 1) // 2 * d, precision=prec)
+                    pk[f"b{blk}.c2.{m}"] = ops.ConvLayer(sd[c2 + ".weight"], sd[c2 + ".bias"], dilation=1,
+                                                         padding=(kr - 1) // 2, precision=prec)
+                    if n["act"] is not None:
+                        for which, idx in (("a1", 2 * m), ("a2", 2 * m + 1)):
+                            a = n["act"].format(blk, idx)
+                            pk[f"b{blk}.{which}.{m}"] = (sd[a + ".alpha"].float().contiguous(), sd[a + ".beta"].float().contiguous())
+        pk["post"] = ops.ConvLayer(sd[n["post"] + ".weight"], sd[n["post"] + ".bias"], padding=(self.kernel_size - 1) // 2,
+                                   precision=prec)
+        if n["act_post"] is not None:
+            pk["post_act"] = (sd[n["act_post"] + ".alpha"].float().contiguous(), sd[n["act_post"] + ".beta"].float().contiguous())
+        self._packed = pk
+        self._buffers_cache = {}
+
+    # -- workspace ---------------------------------------------------------------------------
+    def _workspace(self, b, frames, dev):
+        key = (b, frames, str(dev))
+        ws = self._buffers_cache.get(key)
+        if ws is None:
+            self._buffers_cache.clear()
+            ws = {"h": torch.zeros((b, self.channels, _pad4(frames)), dtype=torch.float32, device=dev)}
+            length = frames
+            for i, u in enumerate(self.upsample_scales):
+                length *= u
+                c = self._stage_channels(i)
+                for name in ("up", "r0", "r1", "sum"):
+                    ws[f"{name}{i}"] = torch.zeros((b, c, _pad4(length)), dtype=torch.float32, device=dev)
+                ws[f"t{i}"] = torch.zeros((b, c, _pad4(length) + 4), dtype=torch.float16, device=dev)
+            ws["wave"] = torch.zeros((b, 1, _pad4(length)), dtype=torch.float32, device=dev)
+            self._buffers_cache[key] = ws
+        return ws
+
+    # -- the generator -----------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_batch(self, c, lengths=None):
+        """c (B,80,F) fp32 CUDA; lengths (B) frames per utterance (int tensor) or None.
+        Returns wave (B, F*prod(scales)) fp32; samples past lengths[b]*384 are unspecified."""
+        if self._packed is None:
+            self.remove_weight_norm()
+        pk = self._packed
+        b, _, frames = c.shape
+        dev = c.device
+        c = c.contiguous().float()
+        ws = self._workspace(b, frames, dev)
+        len_t = lengths.to(device=dev, dtype=torch.int32).contiguous() if lengths is not None else None
+        res_act = ACT_AA_SNAKEBETA if self._names()["act"] is not None else ACT_LEAKY_RELU
+
+        h = pk["pre"](c, len_t, ws["h"], l_in_max=frames)
+        length = frames
+        for i, u in enumerate(self.upsample_scales):
+            up = pk[f"up{i}"](h, len_t, ws[f"up{i}"], l_in_max=length,
+                              act=self.up_act, slope=0.1)
+            length *= u
+            if len_t is not None:
+                len_t = len_t * u
+            total = ws[f"sum{i}"]
+            nblk = len(self.resblock_kernel_sizes)
+            for j in range(nblk):
+                blk = i * nblk + j
+                cur = up
+                ndil = len(self.resblock_dilations[j])
+                for m in range(ndil):
+                    a1 = pk.get(f"b{blk}.a1.{m}", (None, None))
+                    a2 = pk.get(f"b{blk}.a2.{m}", (None, None))
+                    xt = pk[f"b{blk}.c1.{m}"](cur, len_t, ws[f"t{i}"], l_in_max=length, act=res_act, slope=0.1,
+                                              alpha=a1[0], beta=a1[1])
+                    last = m == ndil - 1
+                    if last:  # fold the branch into the multi-receptive-field mean
+                        pk[f"b{blk}.c2.{m}"](xt, len_t, total, l_in_max=length, act=res_act, slope=0.1, alpha=a2[0],
+                                             beta=a2[1], out_alpha=1.0 / nblk, residual=cur, res_beta=1.0 / nblk,
+                                             accumulate=j > 0)
+                    else:
+                        dst = ws[f"r{m % 2}{i}"]
+                        cur = pk[f"b{blk}.c2.{m}"](xt, len_t, dst, l_in_max=length, act=res_act, slope=0.1, alpha=a2[0],
+                                                   beta=a2[1], residual=cur)
+            h = total
+        pa = pk.get("post_act", (None, None))
+        wave = pk["post"](h, len_t, ws["wave"], l_in_max=length, act=self.post_act, slope=0.01, alpha=pa[0], beta=pa[1],
+                          out_act=OUT_TANH)
+        return wave[:, 0, :length]
+
+    def forward(self, c, *args, **kwargs):
+        raise NotImplementedError
+
+
+class HiFiGANGenerator(_GeneratorBase):
+    """InferenceAvocodo.py:6-96."""
+
+    up_act = ACT_LEAKY_RELU
+    post_act = ACT_LEAKY_RELU
+
+    def __init__(self, path_to_weights, in_channels=80, out_channels=1, channels=512, kernel_size=7,
+                 upsample_scales=(8, 6, 4, 2), upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
+                 resblock_dilations=((1, 3, 5), (1, 3, 5), (1, 3, 5)), use_additional_convs=True, bias=True,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, precision="f16"):
+        super().__init__()
+        if not (use_additional_convs and bias and use_weight_norm and nonlinear_activation == "LeakyReLU"
+                and nonlinear_activation_params.get("negative_slope", 0.1) == 0.1 and out_channels == 1):
+            raise ops._lib.EngineError("unsupported HiFiGAN variant (engine covers the reference's inference configuration)")
+        self.in_channels, self.channels, self.kernel_size = in_channels, channels, kernel_size
+        self.upsample_scales, self.upsample_kernel_sizes = tuple(upsample_scales), tuple(upsample_kernel_sizes)
+        self.resblock_kernel_sizes, self.resblock_dilations = tuple(resblock_kernel_sizes), tuple(map(tuple, resblock_dilations))
+        lay, alias = layouts.hifigan_layout(in_channels, out_channels, channels, kernel_size, upsample_scales,
+                                            upsample_kernel_sizes, resblock_kernel_sizes, resblock_dilations)
+        layouts.attach(self, lay, alias)
+        self._init_engine(precision)
+        if path_to_weights is not None:
+            self.load_state_dict(torch.load(path_to_weights, map_location="cpu")["generator"])
+
+    def _names(self):
+        return dict(pre="input_conv", up="upsamples.{}.1", c1="blocks.{}.convs1.{}.1", c2="blocks.{}.convs2.{}.1",
+                    act=None, post="output_conv.1", act_post=None)
+
+    def forward(self, c, normalize_before=False):
+        """c (80,T) -> (T*384,)  (InferenceAvocodo.py:69-80)."""
+        if normalize_before:
+            c = (c - self.mean) / self.scale
+        return self.forward_batch(c.unsqueeze(0)).squeeze()
+
+
+class BigVGAN(_GeneratorBase):
+    """InferenceBigVGAN.py:19-121."""
+
+    up_act = ACT_NONE
+    post_act = ACT_AA_SNAKEBETA
+
+    def __init__(self, path_to_weights, num_mels=80, upsample_initial_channel=512, upsample_rates=(8, 6, 4, 2),
+                 upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
+                 resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), precision="f16"):
+        super().__init__()
+        self.in_channels, self.channels, self.kernel_size = num_mels, upsample_initial_channel, 7
+        self.upsample_scales, self.upsample_kernel_sizes = tuple(upsample_rates), tuple(upsample_kernel_sizes)
+        self.resblock_kernel_sizes, self.resblock_dilations = tuple(resblock_kernel_sizes), tuple(map(tuple, resblock_dilation_sizes))
+        self.num_kernels, self.num_upsamples = len(resblock_kernel_sizes), len(upsample_rates)
+        sd = torch.load(path_to_weights, map_location="cpu")["generator"] if path_to_weights is not None else None
+        # alias_free_torch may or may not have stored its filters as persistent buffers: accept both
+        has_filters = sd is None or any(k.endswith(".filter") for k in sd)
+        lay, alias = layouts.bigvgan_layout(num_mels, upsample_initial_channel, upsample_rates, upsample_kernel_sizes,
+                                            resblock_kernel_sizes, resblock_dilation_sizes, filter_buffers=has_filters)
+        layouts.attach(self, lay, alias)
+        self._init_engine(precision)
+        if sd is not None:
+            self.load_state_dict(sd)
+
+    def _names(self):
+        return dict(pre="conv_pre", up="ups.{}.0", c1="resblocks.{}.convs1.{}", c2="resblocks.{}.convs2.{}",
+                    act="resblocks.{}.activations.{}.act", post="conv_post", act_post="activation_post.act")
+
+    def forward(self, x):
+        """x (80,T) -> (T*384,)  (InferenceBigVGAN.py:72-95)."""
+        return self.forward_batch(x.unsqueeze(0)).squeeze()

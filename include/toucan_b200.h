@@ -1,0 +1,176 @@
+/*
+ * toucan_b200.h -- C ABI of libtoucan_b200.so, the B200 (sm_100a) engine for the
+ * IMS-Toucan hot path: ToucanTTS.inference -> vocoder Generator.
+ *
+ * The reference (PaulMayer123/IMS-Toucan-Prosody-Variance) is pure Python/PyTorch:
+ * the "FFI" it would bind is ctypes from the nn.Module forwards.  Every entry point
+ * below names the reference op group it replaces (paths relative to the reference
+ * root; K-numbers are SURVEY.md section 2.2).
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats.  No torch types.  All pointers are DEVICE
+ *     pointers owned by the caller (tensor.data_ptr()); the library never allocates,
+ *     frees or retains them.  Work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*); no call synchronises the device, so CUDA-graph capture works.
+ *   - return value: 0 ok; <0 library error (TB200_E_*); >0 a cudaError_t.
+ *     tb200_last_error() returns a thread-local human-readable message.
+ *   - activations are "NCL": x[b][c][l], l contiguous, row pitch `ld` elements,
+ *     batch stride `bs` elements.  Ragged batches carry a device int32 array of
+ *     per-utterance valid lengths; positions >= length behave exactly like the
+ *     zero padding a batch-1 reference call would see (no cross-utterance leakage),
+ *     and are never written.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef TOUCAN_B200_H
+#define TOUCAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_VERSION 100
+
+enum {
+  TB200_OK = 0,
+  TB200_E_BADARG = -1,      /* invalid shapes / unsupported configuration            */
+  TB200_E_NOSMEM = -2,      /* configuration does not fit in shared / tensor memory  */
+  TB200_E_NODEVICE = -3     /* no sm_100 device                                      */
+};
+
+/* element types of activation tensors */
+enum { TB200_F32 = 0, TB200_F16 = 1 };
+
+/* tensor-core operand precision of tb200_conv1d */
+enum {
+  TB200_PREC_FP32_SIMT = 0, /* fp32 CUDA-core FMA (exact-parity mode)                          */
+  TB200_PREC_F16 = 1,       /* tcgen05 kind::f16, fp16 operands (10-bit mantissa), fp32 accum  */
+  TB200_PREC_TF32 = 2       /* tcgen05 kind::tf32, fp32 accum                                  */
+};
+
+/* prologue activation applied to the input before the convolution */
+enum {
+  TB200_ACT_NONE = 0,
+  TB200_ACT_LEAKY_RELU = 1, /* HiFiGAN: ResidualBlock.py:83-98, InferenceAvocodo.py:36-43,53   */
+  TB200_ACT_AA_SNAKEBETA = 2, /* BigVGAN: alias_free_torch.Activation1d(SnakeBeta), AMP.py:45-57,
+                                 Snake.py:56-69 -- 2x kaiser-sinc up, x+1/(e^b+1e-9) sin^2(x e^a),
+                                 2x down; replicate padding at the utterance's own ends        */
+  TB200_ACT_RELU = 3,
+  TB200_ACT_SWISH = 4,
+  TB200_ACT_TANH = 5
+};
+
+/* epilogue activation applied to (acc + bias) */
+enum { TB200_OUT_NONE = 0, TB200_OUT_TANH = 1, TB200_OUT_RELU = 2 };
+
+int tb200_version(void);
+const char* tb200_last_error(void);
+/* number of SMs of the current device, or <0 */
+int tb200_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * tb200_conv1d -- implicit-GEMM Conv1d / ConvTranspose1d / Linear (k=1) with fused prologue
+ * activation and fused bias / activation / scale / residual / accumulate epilogue.
+ * Replaces (K3,K5,K6,K8,K9,K10,K11): torch.nn.Conv1d / ConvTranspose1d / Linear call sites in
+ *   InferenceAvocodo.py:69-80, Layers/ResidualBlock.py:83-98          (HiFiGAN generator)
+ *   InferenceBigVGAN.py:72-95, BigVGAN/AMP.py:51-60                   (BigVGAN generator)
+ *   Layers/MultiLayeredConv1d.py:40-51, Convolution.py:43-55, Attention.py:42-64,92
+ *   Layers/DurationPredictor.py:66-77, VariancePredictor.py:67-77, PostNet.py:62-74
+ *   ToucanTTS/Glow.py:248-269,342-365, wavenet.py:89-122
+ *
+ *   y[b][co][t] = out_alpha * OUT( bias[co] + sum_{ci,j} W[co][ci][j] * ACT(x)[b][ci][t - pad + j*dilation] )
+ *               + res_beta * residual[b][co][t]  (+ y_old[b][co][t] if accumulate)
+ * for 0 <= t < len_out[b];  ACT(x) is zero outside [0, len_in[b]).
+ * transposed_stride u > 0 selects ConvTranspose1d(kernel 2u, stride u, padding u/2):
+ *   len_out = u*len_in, weight given as (Cin, Cout, 2u) (torch layout).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tb200_conv1d_params {
+  /* input */
+  const void* x;            /* (B, C_in, L) NCL                                         */
+  int32_t x_dtype;          /* TB200_F32 | TB200_F16                                    */
+  int64_t x_bs;             /* batch stride, elements                                   */
+  int32_t x_ld;             /* row pitch, elements                                      */
+  const int32_t* len_in;    /* (B) valid input lengths, device; NULL = L_in_max for all */
+  int32_t B, C_in, L_in_max;
+  /* convolution */
+  int32_t C_out, K, dilation, pad;
+  int32_t transposed_stride;
+  const void* w_packed;     /* from tb200_pack_conv_weight with the same geometry       */
+  const float* bias;        /* (C_out) or NULL                                          */
+  int32_t precision;        /* TB200_PREC_*                                             */
+  /* prologue */
+  int32_t act;              /* TB200_ACT_*                                              */
+  float act_slope;          /* leaky relu negative slope                                */
+  const float* act_alpha;   /* (C_in) log-scale alpha for AA_SNAKEBETA                  */
+  const float* act_beta;    /* (C_in) log-scale beta                                    */
+  /* epilogue */
+  int32_t out_act;          /* TB200_OUT_*                                              */
+  float out_alpha;
+  const float* residual;    /* (B, C_out, L_out) fp32 or NULL                           */
+  int64_t r_bs; int32_t r_ld;
+  float res_beta;
+  int32_t accumulate;       /* y += ...                                                 */
+  void* y;                  /* (B, C_out, L_out)                                        */
+  int32_t y_dtype; int64_t y_bs; int32_t y_ld;
+} tb200_conv1d_params;
+
+int tb200_conv1d(const tb200_conv1d_params* p, void* stream);
+
+/* Bytes of the packed weight blob for a conv geometry and precision. */
+int64_t tb200_packed_weight_bytes(int32_t C_in, int32_t C_out, int32_t K, int32_t transposed_stride, int32_t precision);
+
+/* Pack torch-layout fp32 weights (device) into the operand image tb200_conv1d streams into
+ * shared memory.  w: (C_out, C_in, K) for Conv1d/Linear, (C_in, C_out, 2u) for ConvTranspose1d.
+ * Load-time only (the fold of weight_g*v/||v|| -- remove_weight_norm,
+ * InferenceAvocodo.py:82-89, InferenceBigVGAN.py:97-105, InferenceToucanTTS.py:321-330 --
+ * happens on the host side before packing). */
+int tb200_pack_conv_weight(const float* w, void* w_packed, int32_t C_in, int32_t C_out, int32_t K,
+                           int32_t transposed_stride, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7 / K12 -- ragged duration rounding, prosody edits, prefix sum, frame expansion.
+ * Integer results are bit-exact with the reference given the same fp32 inputs.
+ * ---------------------------------------------------------------------------------------- */
+
+/* DurationPredictor.py:79  d = clamp(round(exp(x) - 1), 0) (round-half-even), then the edit
+ * loop of InferenceToucanTTS.py:214-225 (word boundary -> 0, silence * pause scale, global
+ * scale; each round(float(d) * s)), then the per-utterance LengthRegulator rescue
+ * (LengthRegulator.py:52-53, batch-1 semantics: an utterance whose durations sum to 0 gets all
+ * ones) and the inclusive prefix sum.  One warp per utterance.
+ *   log_dur   (B, T_ld) fp32 predicted log durations, or NULL when gold_dur is given
+ *   gold_dur  (B, T_ld) int64 external durations or NULL  (not modified; reference mutates)
+ *   text      (B, T_max, 62) fp32 articulatory features (row pitch 62)
+ *   text_len  (B) int32
+ *   dur_out   (B, T_ld) int64 final durations
+ *   cum_out   (B, T_ld) int32 inclusive prefix sums
+ *   frames_out(B) int32 total frames per utterance                                          */
+int tb200_duration_finalize(const float* log_dur, const int64_t* gold_dur, const float* text,
+                            const int32_t* text_len, int32_t B, int32_t T_max, int32_t T_ld,
+                            float pause_scale, float duration_scale,
+                            int64_t* dur_out, int32_t* cum_out, int32_t* frames_out, void* stream);
+
+/* Pitch / energy edits + _scale_variance (InferenceToucanTTS.py:214-218, 226-227, 333-343):
+ * unvoiced (feature 61 == 0) -> pitch 0; non-phoneme (feature 15 == 0) -> energy 0; then
+ * (x - mean_nonzero) * s + mean_nonzero, negatives -> 0, skipped when s == 1.
+ * curve (B, T_ld) fp32 in/out; which: 0 pitch, 1 energy.                                    */
+int tb200_variance_edit(float* curve, const float* text, const int32_t* text_len, int32_t B,
+                        int32_t T_max, int32_t T_ld, int32_t which, float variance_scale, void* stream);
+
+/* LengthRegulator.forward (LengthRegulator.py:37-61, utils.py:475-494) fused with the
+ * pitch/energy embedding add (InferenceToucanTTS.py:230-232):
+ *   out[b][c][f] = enc[b][c][i] + pitch[b][i]*wp[c] + bp[c] + energy[b][i]*we[c] + be[c],
+ *   i = #(cum[b][:] <= f)  (searchsorted right), f < frames[b].
+ * enc NCL (B,C,T) fp32; out NCL (B,C,F) fp32; frame_to_phone (B, F_ld) int32 optional.      */
+int tb200_length_regulate(const float* enc, int64_t enc_bs, int32_t enc_ld,
+                          const float* pitch, const float* energy, int32_t pe_ld,
+                          const float* wp, const float* bp, const float* we, const float* be,
+                          const int32_t* cum, int32_t cum_ld, const int32_t* text_len,
+                          const int32_t* frames, int32_t B, int32_t C, int32_t F_max,
+                          float* out, int64_t out_bs, int32_t out_ld,
+                          int32_t* frame_to_phone, int32_t f2p_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOUCAN_B200_H */
