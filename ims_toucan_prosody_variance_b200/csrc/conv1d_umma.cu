@@ -18,6 +18,7 @@
 // One persistent CTA loops over (utterance, time-tile) pairs; tiles past an utterance's length
 // are skipped, rows past it are staged as zeros (the reference's zero padding at batch 1).
 #include <cstdio>
+#include <cstdlib>
 
 #include "conv_common.cuh"
 
@@ -106,8 +107,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int rows_per_utt_max = a.L_in_max + (a.up > 0 ? 1 : 0);
-
   if (warp == kComputeWarps) {
     // ======================= weight loader warp (TMA bulk copies) =======================
     if (lane == 0) {
@@ -187,8 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
                 const uint32_t a_base = a_row + (uint32_t)(kc * (a.KC / E)) * lbo_a;
                 for (int ks = 0; ks < a.KC / kStepK; ++ks) {
-                  const uint64_t da = make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-                  const uint64_t db = make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+                  const uint64_t da = a.desc_swap ? make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, 128, lbo_a)
+                                                  : make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
+                  const uint64_t db = a.desc_swap ? make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, 128, lbo_b)
+                                                  : make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
                   umma_ss<kTf32>(tmem_base, da, db, idesc, accumulate);
                   accumulate = 1;
                 }
@@ -277,6 +278,10 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   rc = fill_conv_args(p, p->precision, a);
   if (rc) return rc;
 
+  {
+    const char* sw = getenv("TB200_DESC_SWAP");
+    a.desc_swap = (sw && sw[0] == '1') ? 1 : 0;
+  }
   const int bar_bytes = (2 * 256 + 2) * 8 + 16;
   const int scratch_bytes = kComputeWarps * 2 * kAaScratch * 4;
   const int budget = g_max_smem - a.a_bytes - bar_bytes - scratch_bytes - 256;

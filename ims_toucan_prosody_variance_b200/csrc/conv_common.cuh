@@ -42,6 +42,7 @@ struct ConvArgs {
   int tiles_per_utt, total_tiles;
   int tmem_cols;
   int a_bytes;            // staged input tile bytes
+  int desc_swap;          // debug (TB200_DESC_SWAP=1): exchange the LBO / SBO descriptor fields
 };
 
 struct ConvGeom {

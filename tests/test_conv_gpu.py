@@ -1,0 +1,131 @@
+"""tb200_conv1d against torch's CPU conv on the same seeded inputs (all three precisions).
+
+Tolerances: fp32 SIMT 2e-5 relative to the output scale; tf32 / f16 operands have a 10-bit
+mantissa -> 2e-3 of the output RMS (accumulation is fp32 in TMEM)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tf32": 2e-3, "f16": 2e-3}
+
+
+def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0, snake=False, residual=False,
+         out_act=0, out_alpha=1.0, res_beta=1.0, accumulate=False, x_half=False, y_half=False, seed=0):
+    from ims_toucan_prosody_variance_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, L, generator=g)
+    if x_half:
+        x = x.half().float()
+    wshape = (Cin, Cout, 2 * up) if up else (Cout, Cin, K)
+    w = torch.randn(wshape, generator=g) / (Cin * (2 if up else K)) ** 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    alpha = torch.randn(Cin, generator=g) * 0.3
+    beta = torch.randn(Cin, generator=g) * 0.3
+    Lout = L * up if up else L
+    res = torch.randn(B, Cout, Lout, generator=g) if residual else None
+    y0 = torch.randn(B, Cout, Lout, generator=g) if accumulate else torch.zeros(B, Cout, Lout)
+    lens = lens or [L] * B
+    pad = (K - 1) // 2 * dil
+
+    # reference, one utterance at a time on its own length (batch-1 semantics)
+    from oracle import restate
+    ref = y0.clone()
+    for b in range(B):
+        n = lens[b]
+        if n == 0:
+            continue
+        xb = x[b:b + 1, :, :n]
+        if snake:
+            xb = restate.aa_snake(xb, alpha, beta)
+        elif act == 1:
+            xb = F.leaky_relu(xb, slope)
+        if up:
+            o = F.conv_transpose1d(xb, w, bias, stride=up, padding=up // 2)
+        else:
+            o = F.conv1d(xb, w, bias, dilation=dil, padding=pad)
+        if out_act == 1:
+            o = torch.tanh(o)
+        o = o * out_alpha
+        no = n * up if up else n
+        if residual:
+            o = o + res_beta * res[b:b + 1, :, :no]
+        ref[b, :, :no] = o[0] + (y0[b, :, :no] if accumulate else 0)
+
+    layer = ops.ConvLayer(w.to(cuda), bias.to(cuda), dilation=dil, padding=pad, transposed_stride=up, precision=prec)
+    xd = x.to(cuda)
+    if x_half:
+        xd = xd.half()
+    yd = y0.to(cuda)
+    if y_half:
+        yd = yd.half()
+    lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    layer(xd, lt, yd, act=2 if snake else act, slope=slope, alpha=alpha.to(cuda) if snake else None,
+          beta=beta.to(cuda) if snake else None, out_act=out_act, out_alpha=out_alpha,
+          residual=res.to(cuda) if residual else None, res_beta=res_beta, accumulate=accumulate)
+    torch.cuda.synchronize()
+    got = yd.float().cpu()
+    tol = TOL[prec] * (4 if y_half else 1)
+    for b in range(B):
+        no = lens[b] * up if up else lens[b]
+        if no == 0:
+            continue
+        err = (got[b, :, :no] - ref[b, :, :no]).abs().max().item()
+        scale = ref[b, :, :no].pow(2).mean().sqrt().item() + 1e-6
+        assert err / scale < tol * 8, f"{prec} b={b} max err {err:.3e} vs rms {scale:.3e}"
+        rel = ((got[b, :, :no] - ref[b, :, :no]).pow(2).mean().sqrt() / scale).item()
+        assert rel < tol, f"{prec} b={b} rel rms err {rel:.3e}"
+        # positions past the utterance's length must be left untouched
+        assert torch.equal(got[b, :, no:], (y0.half().float() if y_half else y0)[b, :, no:])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "tf32"])
+def test_pointwise_linear(cuda, prec):
+    _run(cuda, prec, B=2, Cin=64, Cout=48, K=1, dil=1, L=300)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "tf32"])
+def test_dilated_conv_residual_ragged(cuda, prec):
+    _run(cuda, prec, B=3, Cin=32, Cout=32, K=11, dil=5, L=400, lens=[400, 131, 7], act=1, slope=0.1, residual=True)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "tf32"])
+def test_conv_k7_odd_channels(cuda, prec):
+    _run(cuda, prec, B=2, Cin=80, Cout=512, K=7, dil=1, L=150, lens=[150, 90])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "tf32"])
+@pytest.mark.parametrize("u,cin,cout", [(8, 64, 32), (6, 32, 16), (2, 64, 32)])
+def test_transposed(cuda, prec, u, cin, cout):
+    _run(cuda, prec, B=2, Cin=cin, Cout=cout, K=2 * u, dil=1, L=200, lens=[200, 77], up=u, act=1, slope=0.1)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "tf32"])
+def test_aa_snake_prologue(cuda, prec):
+    _run(cuda, prec, B=2, Cin=32, Cout=32, K=3, dil=3, L=300, lens=[300, 45], snake=True, residual=True)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_epilogue_variants(cuda, prec):
+    _run(cuda, prec, B=2, Cin=32, Cout=16, K=7, dil=1, L=260, lens=[260, 129], act=1, slope=0.01, out_act=1)
+    _run(cuda, prec, B=2, Cin=64, Cout=64, K=3, dil=1, L=260, lens=[260, 128], residual=True, out_alpha=1 / 3,
+         res_beta=1 / 3, accumulate=True)
+    _run(cuda, prec, B=1, Cin=64, Cout=64, K=3, dil=1, L=260, x_half=True, y_half=True)
+
+
+@pytest.mark.parametrize("prec", ["f16", "tf32"])
+def test_streamed_weights_wide(cuda, prec):
+    # 256x256x11 does not fit in shared memory: exercises the weight ring and multi-chunk K loop
+    _run(cuda, prec, B=2, Cin=256, Cout=256, K=11, dil=1, L=300, lens=[300, 200], act=1, slope=0.1)
+
+
+@pytest.mark.parametrize("prec", ["f16"])
+def test_transposed_wide_multi_ntile(cuda, prec):
+    # N = 256*8 = 2048 -> 8 accumulator tiles per input tile
+    _run(cuda, prec, B=1, Cin=512, Cout=256, K=16, dil=1, L=140, up=8)
+
+
+def test_single_tap_tiny(cuda):
+    for prec in ("fp32", "f16", "tf32"):
+        _run(cuda, prec, B=1, Cin=16, Cout=16, K=1, dil=1, L=5)
