@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the IMS-Toucan hot path on B200: audio-seconds/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
+
+Workload (BASELINE.json configs[1]): BigVGAN generator alone, batch 64 synthetic 80-bin mel
+spectrograms x 500 frames -> 24 kHz wave (512 s of audio per step per GPU).  One process per GPU;
+under torchrun every rank synthesises its own shard of 64 utterances (weak scaling, no collective on
+the data path; NCCL only gathers output lengths and the max-over-ranks time).
+
+Prints ONE JSON line (see the contract in the task description): `value` is device-timed with the
+mels resident in HBM, `e2e` goes through the module's public batched call with pinned HOST buffers
+(H2D of the mels and D2H of the waveforms inside the timed region), `roofline` is the tensor-core
+roofline of the conv kernel, `cpu_baseline` is the oracle port of the reference timed on this box's
+host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_FRAME = 648_241_152          # 2*MAC of every Conv1d/ConvTranspose1d of the generator
+SAMPLES_PER_FRAME = 384
+SAMPLE_RATE = 24_000
+METRIC = "audio-seconds/sec"
+UNIT = "audio_s/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons))
+        return out
+
+
+def build_generator(kind, precision, device):
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory  # weights factory only (state_dict values); not on the timed path
+    sd = factory.make_state_dict(kind, 1234)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "g.pt")
+        torch.save({"generator": sd}, path)
+        cls = tb.BigVGAN if kind == "bigvgan" else tb.HiFiGANGenerator
+        model = cls(path, precision=precision).to(device)
+    model.remove_weight_norm()
+    return model, sd
+
+
+def cpu_reference_step(kind, fsd, mel):
+    from oracle import restate
+    fwd = restate.bigvgan_forward if kind == "bigvgan" else restate.hifigan_forward
+    with torch.inference_mode():
+        return fwd(fsd, mel)
+
+
+def time_cpu(kind, sd, frames, repeats, warmup):
+    """Oracle port of the reference on the host cores; sequential batch-1 like read_to_file
+    (ToucanTTSInterface.py:269-280).  Returns audio-s/s and the sample description."""
+    from oracle import factory, restate
+    torch.set_num_threads(os.cpu_count() or 1)
+    fsd = restate.fold_weight_norm(sd)
+    mel = factory.make_mel(1, frames, seed=2)[0]
+    for _ in range(warmup):
+        cpu_reference_step(kind, fsd, mel)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_reference_step(kind, fsd, mel)
+        best = min(best, time.perf_counter() - t0)
+    audio = frames * SAMPLES_PER_FRAME / SAMPLE_RATE
+    return audio / best, best, f"1 utterance x {frames} frames ({audio:.1f} s audio), batch-1, best of {repeats}"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    Python and does not travel to the GPU box) with all host threads, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import factory
+    sd = factory.make_state_dict(args.vocoder, 1234)
+    cores = os.cpu_count() or 1
+    val, best, sample = time_cpu(args.vocoder, sd, args.frames, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(best * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"{'BigVGAN' if args.vocoder == 'bigvgan' else 'HiFiGAN'} generator alone: batch {args.batch} "
+                        f"synthetic 80-bin mels x {args.frames} frames -> 24 kHz wave (per GPU)",
+            "batch_per_gpu": args.batch, "frames": args.frames, "vocoder": args.vocoder,
+            "operand_precision": args.precision, "weights": "random-init (oracle.factory seed 1234)",
+            "l2": "working set per step (>6 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--vocoder", default="bigvgan", choices=["bigvgan", "hifigan"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ims_toucan_prosody_variance_b200 import ops
+    from oracle import factory
+    model, sd = build_generator(args.vocoder, args.precision, dev)
+    mel_host = factory.make_mel(args.batch, args.frames, seed=100 + rank).pin_memory()
+    mel_dev = mel_host.to(dev)
+    lengths = torch.full((args.batch,), args.frames, dtype=torch.int32)
+    n_samples = args.frames * SAMPLES_PER_FRAME
+    wave_host = torch.empty((args.batch, n_samples), dtype=torch.float32).pin_memory()
+    audio_s_per_step = args.batch * n_samples / SAMPLE_RATE
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        model.forward_batch(mel_dev, lengths)
+    barrier()
+    launches0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        wave = model.forward_batch(mel_dev, lengths)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (ops.LAUNCHES - launches0) // args.steps
+    ms_step = ms_total / args.steps
+    value = world * audio_s_per_step / (ms_step / 1e3)
+
+    # ---- end to end through the public call with host buffers ----
+    def e2e_step():
+        m = mel_host.to(dev, non_blocking=True)
+        w = model.forward_batch(m, lengths)
+        wave_host.copy_(w, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    e2e_value = world * audio_s_per_step / (ms_e2e / 1e3)
+
+    # ---- NCCL: gather output lengths (the only collective of the path) ----
+    out_lengths = (lengths.to(dev) * SAMPLES_PER_FRAME).to(torch.int64)
+    if dist is not None:
+        gathered = [torch.empty_like(out_lengths) for _ in range(world)]
+        dist.all_gather(gathered, out_lengths)
+        total_samples = int(sum(int(g.sum()) for g in gathered))
+    else:
+        total_samples = int(out_lengths.sum())
+    assert total_samples == world * args.batch * n_samples
+    finite = bool(torch.isfinite(wave).all()) and float(wave.abs().max()) <= 1.0
+    if not finite:
+        raise SystemExit("bench.py: generator produced non-finite or out-of-range samples")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    tflops_peak, hbm_peak, peak_src = peaks()
+    flops_step = FLOP_PER_FRAME * args.batch * args.frames
+    achieved = flops_step / (ms_step / 1e3) / 1e12  # per GPU: each rank does the same work in ms_step
+    roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": tflops_peak, "unit": "TFLOP/s",
+                "frac": round(achieved / tflops_peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel": "conv1d_umma_kernel (all conv launches of one step; algorithmic FLOPs = "
+                          f"{FLOP_PER_FRAME} per mel frame x {args.batch * args.frames} frames)"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, best, sample = time_cpu(args.vocoder, sd, args.frames, 2, 1)
+        cpu = {"value": round(v, 3), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"f16": "fp16", "tf32": "tf32", "fp32": "fp32"}[args.precision], "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
+                "d2h_bytes_per_step": wave_host.numel() * 4, "ms_per_step": round(ms_e2e, 4)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "vocoder_rtf": round((ms_step / 1e3) / audio_s_per_step, 8),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

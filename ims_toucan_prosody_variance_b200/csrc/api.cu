@@ -140,7 +140,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       }
     }
     if constexpr (sizeof(T) == 2) out[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-    else out[i] = v;
+    else out[i] = round_tf32(v);
   }
 }
 

@@ -59,7 +59,8 @@ struct UmmaStore {
       u.w = *reinterpret_cast<uint32_t*>(&h3);
       *reinterpret_cast<uint4*>(dst) = u;
     } else {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      // the tensor core truncates fp32 operands to tf32: round to nearest here instead
+      *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
     }
   }
 };
@@ -186,10 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
                 const uint32_t a_base = a_row + (uint32_t)(kc * (a.KC / E)) * lbo_a;
                 for (int ks = 0; ks < a.KC / kStepK; ++ks) {
-                  const uint64_t da = a.desc_swap ? make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, 128, lbo_a)
-                                                  : make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-                  const uint64_t db = a.desc_swap ? make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, 128, lbo_b)
-                                                  : make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+                  const uint64_t da = make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
+                  const uint64_t db = make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
                   umma_ss<kTf32>(tmem_base, da, db, idesc, accumulate);
                   accumulate = 1;
                 }
@@ -278,10 +277,6 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   rc = fill_conv_args(p, p->precision, a);
   if (rc) return rc;
 
-  {
-    const char* sw = getenv("TB200_DESC_SWAP");
-    a.desc_swap = (sw && sw[0] == '1') ? 1 : 0;
-  }
   const int bar_bytes = (2 * 256 + 2) * 8 + 16;
   const int scratch_bytes = kComputeWarps * 2 * kAaScratch * 4;
   const int budget = g_max_smem - a.a_bytes - bar_bytes - scratch_bytes - 256;

@@ -42,7 +42,6 @@ struct ConvArgs {
   int tiles_per_utt, total_tiles;
   int tmem_cols;
   int a_bytes;            // staged input tile bytes
-  int desc_swap;          // debug (TB200_DESC_SWAP=1): exchange the LBO / SBO descriptor fields
 };
 
 struct ConvGeom {
@@ -87,6 +86,12 @@ __device__ __forceinline__ float load_x(const void* x, bool f16, long long idx) 
 }
 
 __device__ __forceinline__ float clamp_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 
 __device__ __forceinline__ float apply_pointwise(float v, int act, float slope) {
   switch (act) {

@@ -91,7 +91,10 @@ class _GeneratorBase(torch.nn.Module):
                 c = self._stage_channels(i)
                 for name in ("up", "r0", "r1", "sum"):
                     ws[f"{name}{i}"] = torch.zeros((b, c, _pad4(length)), dtype=torch.float32, device=dev)
-                ws[f"t{i}"] = torch.zeros((b, c, _pad4(length) + 4), dtype=torch.float16, device=dev)
+                # value between the two convs of a residual pair: an MMA operand only -> fp16 in the
+                # fp16-operand mode, fp32 otherwise
+                tdt = torch.float16 if self.precision == "f16" else torch.float32
+                ws[f"t{i}"] = torch.zeros((b, c, _pad4(length) + 4), dtype=tdt, device=dev)
             ws["wave"] = torch.zeros((b, 1, _pad4(length)), dtype=torch.float32, device=dev)
             self._buffers_cache[key] = ws
         return ws

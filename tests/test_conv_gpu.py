@@ -66,7 +66,7 @@ def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0,
           residual=res.to(cuda) if residual else None, res_beta=res_beta, accumulate=accumulate)
     torch.cuda.synchronize()
     got = yd.float().cpu()
-    tol = TOL[prec] * (4 if y_half else 1)
+    tol = max(TOL[prec], 1e-3) if y_half else TOL[prec]  # fp16 output rounding: 2^-11 relative
     for b in range(B):
         no = lens[b] * up if up else lens[b]
         if no == 0:

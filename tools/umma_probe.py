@@ -33,7 +33,7 @@ for prec in %r:
     run(prec, 256, 256, 3, 300)
 '''
 
-for swap in ("0", "1"):
+for swap in ("0",):
     for precs in (("f16",), ("tf32",)):
         print(f"== TB200_DESC_SWAP={swap} {precs}", flush=True)
         env = dict(os.environ, TB200_DESC_SWAP=swap)
