@@ -110,6 +110,7 @@ int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a) {
   a.total_tiles = a.tiles_per_utt * p->B;
   a.tmem_cols = next_pow2_cols(a.NT);
   a.a_bytes = (a.Cin_pad / g.epc) * a.R * 16;
+  a.S = 1; a.a_bufs = 1; a.acc_bufs = 1; a.n_panels = 1; a.aa_fast = 0;
   return 0;
 }
 

@@ -1,22 +1,29 @@
 // conv1d_umma.cu -- implicit-GEMM Conv1d / ConvTranspose1d on the sm_100a tensor cores.
 //
 //   GEMM view (per utterance b):   D[t, n] = sum_{tap j} sum_{ci} A_j[t, ci] * W_j[n, ci]
-//     M = time (128 output rows per tile == 128 TMEM lanes), N = output channels (<= 256 per
+//     M = time (128 rows per accumulator == 128 TMEM lanes), N = output channels (<= 256 per
 //     accumulator), K = input channels, one pass over K per tap.
-//   A operand: ONE staged tile of ACT(x) for rows [t0 - halo_l, t0 + 128 + halo_r), written by the
+//   A operand: ONE staged tile of ACT(x) for rows [t0 - halo_l, t0 + S*128 + halo_r), written by the
 //     producer warps in the canonical K-major SWIZZLE_NONE layout with 16 B per row
-//     ([Cin/E][R][E] elements).  Because rows are linear in that layout, tap j is the same tile
-//     read through a descriptor whose start address is shifted by tap_off[j] rows: no im2col, no
-//     per-tap reload.  The activation (LeakyReLU, or BigVGAN's anti-aliased SnakeBeta = 2x
-//     kaiser-sinc up, snake, 2x down) is fused into the staging, so it never touches HBM.
+//     ([Cin/E][R][E] elements).  Rows are linear in that layout, so tap j of sub-tile s is the same
+//     tile read through a descriptor whose start address is shifted by (s*128 + tap_off[j]) rows: no
+//     im2col, no per-tap reload.  The activation (LeakyReLU, or BigVGAN's anti-aliased SnakeBeta =
+//     2x kaiser-sinc up, snake, 2x down) is fused into the staging and never touches HBM.
 //   B operand: weight blocks [KC/E][NT][E] pre-packed at load time, brought in by the TMA engine
-//     (cp.async.bulk + mbarrier), resident for the CTA's lifetime when they fit, else streamed
-//     through a ring that tcgen05.commit releases.
-//   D: fp32 in TMEM; epilogue = tcgen05.ld -> bias / activation / scale / residual / accumulate ->
-//     coalesced NCL stores (a warp writes 32 consecutive time steps of one channel).
+//     (cp.async.bulk + mbarrier); resident for the CTA's lifetime when they fit, else streamed
+//     through a ring released by tcgen05.commit.  One block serves all S sub-tiles.
+//   D: fp32 in TMEM, double buffered; epilogue = tcgen05.ld -> bias / activation / scale / residual /
+//     accumulate -> coalesced NCL stores (a warp writes 32 consecutive time steps of one channel).
 //
-// One persistent CTA loops over (utterance, time-tile) pairs; tiles past an utterance's length
-// are skipped, rows past it are staged as zeros (the reference's zero padding at batch 1).
+// Warp roles (one persistent CTA per SM, 18 warps):
+//   warps 0-7   producers : stage A[buf] (double buffered), arrive a_full
+//   warp  8     MMA issuer: one elected thread issues tcgen05.mma, commits to a_empty / acc_full / w_empty
+//   warp  9     weight loader (TMA bulk copies)
+//   warps 10-17 epilogue  : drain accumulator buffer, arrive acc_empty
+// so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+//
+// Tiles past an utterance's length are skipped, rows past it are staged as zeros (the zero padding a
+// batch-1 reference call sees).
 #include <cstdio>
 #include <cstdlib>
 
@@ -24,8 +31,13 @@
 
 namespace tb200 {
 
-constexpr int kComputeWarps = 8;
-constexpr int kThreads = (kComputeWarps + 1) * 32;  // + 1 weight-loader warp
+constexpr int kProdWarps = 8;
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = kProdWarps;
+constexpr int kLoadWarp = kProdWarps + 1;
+constexpr int kEpiWarp0 = kProdWarps + 2;
+constexpr int kThreads = (kProdWarps + 2 + kEpiWarps) * 32;  // 576
+constexpr int kMaxRing = 64;
 
 template <typename T>
 struct ElemTraits;
@@ -39,6 +51,21 @@ struct ElemTraits<float> {
   static constexpr int kEpc = 4;
   static constexpr bool kTf32 = true;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T to_operand(float v);
+template <>
+__device__ __forceinline__ __half to_operand<__half>(float v) {
+  return __float2half_rn(clamp_f16(v));
+}
+template <>
+__device__ __forceinline__ float to_operand<float>(float v) {
+  return round_tf32(v);  // the tensor core would truncate fp32 -> tf32; round to nearest instead
+}
 
 // A-tile store policy: 16-byte group g, row r -> canonical K-major SWIZZLE_NONE position.
 template <typename T>
@@ -59,44 +86,199 @@ struct UmmaStore {
       u.w = *reinterpret_cast<uint32_t*>(&h3);
       *reinterpret_cast<uint4*>(dst) = u;
     } else {
-      // the tensor core truncates fp32 operands to tf32: round to nearest here instead
       *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
     }
   }
 };
 
 // ---------------------------------------------------------------------------------------------
-// epilogue for one 16-column slab held in registers
+// producer, pointwise activations: lane = time (coalesced 128-byte rows), branch-free loads with
+// clamped addresses, the next task's loads in flight while the current one is converted/stored.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void stage_pointwise_mlp(const ConvArgs& a, int b, int t_lo, int g0, int ng, int len, T* smA,
+                                                    int pw, int lane) {
+  constexpr int E = ElemTraits<T>::kEpc;
+  const int R = a.R;
+  const int nrb = (R + 31) / 32;
+  const int ntask = ng * nrb;
+  const long long xb = (long long)b * a.x_bs;
+  const UmmaStore<T> st{smA, R};
+  float cur[E], nxt[E];
+  auto issue = [&](int task, float (&r)[E]) {
+    const int g = task / nrb, rb = task - g * nrb;
+    const int t = min(max(t_lo + rb * 32 + lane, 0), len - 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int c = min((g0 + g) * E + e, a.Cin - 1);
+      r[e] = load_x(a.x, a.x_f16, xb + (long long)c * a.x_ld + t);
+    }
+  };
+  int task = pw;
+  if (task < ntask) issue(task, cur);
+  for (; task < ntask; task += kProdWarps) {
+    if (task + kProdWarps < ntask) issue(task + kProdWarps, nxt);
+    const int g = task / nrb, rb = task - g * nrb;
+    const int r = rb * 32 + lane;
+    const int t = t_lo + r;
+    const bool valid = (t >= 0) && (t < len);
+    float v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float av = apply_pointwise(cur[e], a.act, a.slope);
+      v[e] = (valid && (g0 + g) * E + e < a.Cin) ? av : 0.f;
+    }
+    if (r < R) st(g, r, v);
+#pragma unroll
+    for (int e = 0; e < E; ++e) cur[e] = nxt[e];
+  }
+}
 
+// ---------------------------------------------------------------------------------------------
+// producer, anti-aliased SnakeBeta, interior tiles: lane = channel, sequential in time with register
+// sliding windows (8 inputs, 8 (s_even, s_odd) pairs) -> one 16-byte load per 4 (fp32) / 8 (fp16)
+// steps per lane, 24 filter FMAs + 2 sin per output, no scratch, no intra-warp exchange.
+//   stream step n (absolute time): ingest x[n]; pair(n-3) = snake(up-filter around n-3);
+//   out(n-6) = down-filter over pairs n-9 .. n-3.
+// A warp task = (32-channel block, row segment).  Requires every touched x index inside [0, len).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const void* x, bool f16, long long idx, float (&r)[8]) {
+  if (f16) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + idx));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f2 = __half22float2(h[i]);
+      r[2 * i] = f2.x;
+      r[2 * i + 1] = f2.y;
+    }
+  } else {
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + idx));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + idx + 4));
+    r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = p0.w;
+    r[4] = p1.x; r[5] = p1.y; r[6] = p1.z; r[7] = p1.w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_aa_channel(const ConvArgs& a, int b, int t_lo, int cb0, int ncb, int nseg, T* smA,
+                                                 int pw, int lane) {
+  constexpr int E = ElemTraits<T>::kEpc;
+  const int R = a.R;
+  const int seg_rows = (R + nseg - 1) / nseg;
+  const long long xb = (long long)b * a.x_bs;
+  for (int task = pw; task < ncb * nseg; task += kProdWarps) {
+    const int cb = task / nseg, seg = task - cb * nseg;
+    const int r_beg = seg * seg_rows;
+    const int r_end = min(R, r_beg + seg_rows);
+    if (r_beg >= r_end) continue;
+    const int cl = cb * 32 + lane;          // channel inside this staged panel
+    const int c = cb0 * 32 + cl;            // absolute input channel
+    const int t_beg = t_lo + r_beg, t_end = t_lo + r_end;
+    const int ts = (t_beg - 9) & ~7;        // first ingested step, 16-byte aligned
+    const long long row = xb + (long long)c * a.x_ld;
+    const float ea = __expf(__ldg(a.alpha + c));
+    const float ib = 1.0f / (__expf(__ldg(a.beta + c)) + 1e-9f);
+    T* dst = smA + ((long long)(cl / E) * R) * E + (cl % E);
+
+    float xw[8], sv[16], cur[8], n1[8], n2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xw[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+    load8(a.x, a.x_f16, row + ts, cur);
+    load8(a.x, a.x_f16, row + ts + 8, n1);
+    for (int base = ts; base - 6 < t_end; base += 8) {
+      load8(a.x, a.x_f16, row + base + 16, n2);  // look-ahead stays inside the utterance: see `interior`
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = base + j;
+        xw[j] = cur[j];
+        if (n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
+          float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            u0 = fmaf(xw[(j + 2 + q) & 7], c_aa_filter[11 - 2 * q], u0);   // x[n-6+q]
+            u1 = fmaf(xw[(j + 3 + q) & 7], c_aa_filter[10 - 2 * q], u1);   // x[n-5+q]
+          }
+          u0 *= 2.f;
+          u1 *= 2.f;
+          const float z0 = __sinf(u0 * ea), z1 = __sinf(u1 * ea);
+          sv[2 * ((j + 5) & 7)] = fmaf(ib * z0, z0, u0);
+          sv[2 * ((j + 5) & 7) + 1] = fmaf(ib * z1, z1, u1);
+        }
+        const int t = n - 6;
+        if (t >= t_beg && t < t_end) {
+          float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
+            o0 = fmaf(c_aa_filter[k], sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
+            o1 = fmaf(c_aa_filter[k + 1], sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
+          }
+          dst[(long long)(t - t_lo) * E] = to_operand<T>(o0 + o1);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cur[i] = n1[i];
+        n1[i] = n2[i];
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool kFast>
+struct WsLayout {  // shared-memory carve-up, computed identically on host and device
+  int a_off, w_off, bar_off, tmem_off, scratch_off, total;
+};
+__host__ __device__ inline WsLayout ws_layout(const ConvArgs& a) {
+  WsLayout l;
+  l.a_off = 0;
+  l.w_off = a.a_bufs * a.a_bytes;
+  l.bar_off = l.w_off + a.ring_slots * a.chunk_bytes;
+  const int nbars = 2 * a.ring_slots + 2 * a.a_bufs + 2 * a.acc_bufs;
+  l.tmem_off = l.bar_off + nbars * 8;
+  l.scratch_off = l.tmem_off + 16;
+  l.total = l.scratch_off + kProdWarps * 2 * kAaScratch * 4;
+  return l;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int E = ElemTraits<T>::kEpc;
   constexpr bool kTf32 = ElemTraits<T>::kTf32;
   constexpr int kStepK = 2 * E;  // K per tcgen05.mma
 
   extern __shared__ __align__(128) uint8_t smem[];
-  T* smA = reinterpret_cast<T*>(smem);
-  uint8_t* smW = smem + a.a_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smW + (long long)a.ring_slots * a.chunk_bytes);
-  uint64_t* empty_bar = full_bar + a.ring_slots;
-  uint64_t* acc_bar = empty_bar + a.ring_slots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  float* scratch = reinterpret_cast<float*>(tmem_slot + 2);
+  const WsLayout lay = ws_layout(a);
+  uint8_t* smW = smem + lay.w_off;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* w_empty = w_full + a.ring_slots;
+  uint64_t* a_full = w_empty + a.ring_slots;
+  uint64_t* a_empty = a_full + a.a_bufs;
+  uint64_t* acc_full = a_empty + a.a_bufs;
+  uint64_t* acc_empty = acc_full + a.acc_bufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + lay.tmem_off);
+  float* scratch = reinterpret_cast<float*>(smem + lay.scratch_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < a.ring_slots; ++i) {
-        mbar_init(full_bar + i, 1);
-        mbar_init(empty_bar + i, 1);
+        mbar_init(w_full + i, 1);
+        mbar_init(w_empty + i, 1);
       }
-      mbar_init(acc_bar, 1);
+      for (int i = 0; i < a.a_bufs; ++i) {
+        mbar_init(a_full + i, 1);
+        mbar_init(a_empty + i, 1);
+      }
+      for (int i = 0; i < a.acc_bufs; ++i) {
+        mbar_init(acc_full + i, 1);
+        mbar_init(acc_empty + i, kEpiWarps);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -108,134 +290,219 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kComputeWarps) {
-    // ======================= weight loader warp (TMA bulk copies) =======================
+  const int rows_tile = a.S * kTileM;
+  const int extra_row = a.up > 0 ? 1 : 0;
+  const bool restage_per_nt = a.n_panels > 1;   // the A buffer holds one channel panel only
+  const int kc_per_panel = a.n_kchunks / a.n_panels;
+  const int groups_per_panel = kc_per_panel * (a.KC / E);
+
+  if (warp < kProdWarps) {
+    // ================================ producers ================================
+    uint32_t ai = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_utt;
+      const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
+      const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+      if (t0 >= len + extra_row || len <= 0) continue;
+      const int t_lo = t0 - a.halo_l;
+      for (int nt = 0; nt < a.n_ntiles; ++nt) {
+        if (!restage_per_nt && nt > 0) break;
+        for (int pn = 0; pn < a.n_panels; ++pn, ++ai) {
+          const int buf = ai % a.a_bufs;
+          mbar_wait(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
+          T* smA = reinterpret_cast<T*>(smem + lay.a_off + buf * a.a_bytes);
+          const int g0 = pn * groups_per_panel;
+          if (a.act == TB200_ACT_AA_SNAKEBETA) {
+            // fast path: whole staged range (plus filter reach and load look-ahead) inside the utterance
+            const bool interior = a.aa_fast && (t_lo - 16 >= 0) && (t_lo + a.R + 32 <= len);
+            if (interior) {
+              const int ncb = groups_per_panel * E / 32;
+              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, max(1, kProdWarps / ncb), smA, warp, lane);
+            } else {
+              const UmmaStore<T> st{smA, a.R};
+              stage_aa_snake<E, true>(a, b, t_lo, a.R, g0, groups_per_panel, len, st, scratch, warp, kProdWarps, lane);
+            }
+          } else {
+            stage_pointwise_mlp<T>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory");
+          if (threadIdx.x == 0) mbar_arrive(a_full + buf);
+        }
+      }
+    }
+  } else if (warp == kLoadWarp) {
+    // ================================ weight loader ================================
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w);
       if (a.resident) {
         for (int c = 0; c < a.n_chunks; ++c) {
-          mbar_arrive_expect_tx(full_bar + c, a.chunk_bytes);
-          bulk_copy_g2s(smW + (long long)c * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes, full_bar + c);
+          mbar_arrive_expect_tx(w_full + c, a.chunk_bytes);
+          bulk_copy_g2s(smW + (long long)c * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes, w_full + c);
         }
       } else {
         uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
           const int b = tile / a.tiles_per_utt;
-          const int t0 = (tile - b * a.tiles_per_utt) * kTileM;
+          const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
           const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
-          const int rows = len + (a.up > 0 ? 1 : 0);
-          if (t0 >= rows || len <= 0) continue;
-          for (int c = 0; c < a.n_chunks; ++c, ++cc) {
-            const int slot = cc % a.ring_slots;
-            const uint32_t ph = (cc / a.ring_slots) & 1;
-            mbar_wait(empty_bar + slot, ph ^ 1);
-            mbar_arrive_expect_tx(full_bar + slot, a.chunk_bytes);
-            bulk_copy_g2s(smW + (long long)slot * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes,
-                          full_bar + slot);
-          }
+          if (t0 >= len + extra_row || len <= 0) continue;
+          for (int nt = 0; nt < a.n_ntiles; ++nt)
+            for (int pn = 0; pn < a.n_panels; ++pn)
+              for (int j = 0; j < a.ntaps; ++j)
+                for (int kcl = 0; kcl < kc_per_panel; ++kcl, ++cc) {
+                  const int c = (nt * a.ntaps + j) * a.n_kchunks + pn * kc_per_panel + kcl;
+                  const int slot = cc % a.ring_slots;
+                  mbar_wait(w_empty + slot, ((cc / a.ring_slots) & 1) ^ 1);
+                  mbar_arrive_expect_tx(w_full + slot, a.chunk_bytes);
+                  bulk_copy_g2s(smW + (long long)slot * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes,
+                                w_full + slot);
+                }
         }
       }
     }
-  } else {
-    // ======================= compute warps: stage A, issue MMA, epilogue =======================
-    const uint32_t idesc = make_instr_desc(a.NT, kTf32);
-    const uint32_t lbo_a = a.R * 16, lbo_b = a.NT * 16;
-    const uint32_t smA_u = smem_u32(smA), smW_u = smem_u32(smW);
-    uint32_t cc = 0;        // running weight-block counter (ring position; issuer thread only)
-    uint32_t acc_cnt = 0;   // accumulators completed so far (acc_bar phase)
-    bool first_tile = true;
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half_id = warp >> 2;     // column half handled by this warp
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const int b = tile / a.tiles_per_utt;
-      const int t0 = (tile - b * a.tiles_per_utt) * kTileM;
-      const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
-      const int rows = len + (a.up > 0 ? 1 : 0);
-      if (t0 >= rows || len <= 0) continue;
-      const int len_out = a.up > 0 ? len * a.up : len;
-
-      // ---- stage the activated input tile ----
-      {
-        UmmaStore<T> st{smA, a.R};
-        if (a.act == TB200_ACT_AA_SNAKEBETA)
-          stage_aa_snake<E, kFast>(a, b, t0 - a.halo_l, a.R, 0, a.Cin_pad / E, len, st, scratch, warp, kComputeWarps, lane);
-        else
-          stage_pointwise<E>(a, b, t0 - a.halo_l, a.R, 0, a.Cin_pad / E, len, st, warp, kComputeWarps, lane);
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
-
-      for (int nt = 0; nt < a.n_ntiles; ++nt) {
-        // ---- MMA issue: one elected thread ----
-        if (warp == 0) {
-          if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(a.NT, kTf32);
+      const uint32_t lbo_a = a.R * 16, lbo_b = a.NT * 16;
+      const uint32_t smW_u = smem_u32(smW);
+      uint32_t ai = 0, ac = 0, cc = 0;
+      bool first_tile = true;
+      uint32_t a_buf_cur = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_utt;
+        const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
+        const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+        const int rows = len + extra_row;
+        if (t0 >= rows || len <= 0) continue;
+        const int nsub = min(a.S, (rows - t0 + kTileM - 1) / kTileM);
+        for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
+          const int abuf = ac % a.acc_bufs;
+          mbar_wait(acc_empty + abuf, ((ac / a.acc_bufs) & 1) ^ 1);
+          const uint32_t acc_col = tmem_base + (uint32_t)(abuf * a.S * a.NT);
+          for (int pn = 0; pn < a.n_panels; ++pn) {
+            if (restage_per_nt || nt == 0) {
+              a_buf_cur = ai % a.a_bufs;
+              mbar_wait(a_full + a_buf_cur, (ai / a.a_bufs) & 1);
+              ++ai;
+            }
             tc_fence_after();
-            uint32_t accumulate = 0;
+            const uint32_t smA_u = smem_u32(smem + lay.a_off + a_buf_cur * a.a_bytes);
             for (int j = 0; j < a.ntaps; ++j) {
               const uint32_t a_row = smA_u + (uint32_t)(a.tap_off[j] + a.halo_l) * 16u;
-              for (int kc = 0; kc < a.n_kchunks; ++kc) {
-                const int c = (nt * a.ntaps + j) * a.n_kchunks + kc;
+              for (int kcl = 0; kcl < kc_per_panel; ++kcl, ++cc) {
                 int slot;
                 if (a.resident) {
-                  slot = c;
-                  if (first_tile) mbar_wait(full_bar + slot, 0);
+                  slot = (nt * a.ntaps + j) * a.n_kchunks + pn * kc_per_panel + kcl;
+                  if (first_tile) mbar_wait(w_full + slot, 0);
                 } else {
                   slot = cc % a.ring_slots;
-                  mbar_wait(full_bar + slot, (cc / a.ring_slots) & 1);
+                  mbar_wait(w_full + slot, (cc / a.ring_slots) & 1);
                 }
                 tc_fence_after();
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
-                const uint32_t a_base = a_row + (uint32_t)(kc * (a.KC / E)) * lbo_a;
-                for (int ks = 0; ks < a.KC / kStepK; ++ks) {
-                  const uint64_t da = make_smem_desc(a_base + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-                  const uint64_t db = make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-                  umma_ss<kTf32>(tmem_base, da, db, idesc, accumulate);
-                  accumulate = 1;
+                const uint32_t a_base = a_row + (uint32_t)(kcl * (a.KC / E)) * lbo_a;
+                const uint32_t fresh = (pn == 0 && j == 0 && kcl == 0) ? 0u : 1u;
+                for (int sub = 0; sub < nsub; ++sub) {
+                  for (int ks = 0; ks < a.KC / kStepK; ++ks) {
+                    const uint64_t da = make_smem_desc(a_base + (uint32_t)(sub * kTileM) * 16u + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
+                    const uint64_t db = make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+                    umma_ss<kTf32>(acc_col + (uint32_t)(sub * a.NT), da, db, idesc, (ks == 0) ? fresh : 1u);
+                  }
                 }
-                if (!a.resident) umma_commit(empty_bar + slot);
-                ++cc;
+                if (!a.resident) umma_commit(w_empty + slot);
               }
             }
-            umma_commit(acc_bar);
+            if (restage_per_nt || nt == a.n_ntiles - 1) umma_commit(a_empty + a_buf_cur);
           }
-          __syncwarp();
+          umma_commit(acc_full + abuf);
         }
-
-        // ---- epilogue: TMEM -> registers -> global ----
-        mbar_wait(acc_bar, acc_cnt & 1);
-        ++acc_cnt;
+        first_tile = false;
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half_id = ew >> 2;       // which half of the column slabs
+    uint32_t ac = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_utt;
+      const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
+      const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+      const int rows = len + extra_row;
+      if (t0 >= rows || len <= 0) continue;
+      const int len_out = a.up > 0 ? len * a.up : len;
+      const int nsub = min(a.S, (rows - t0 + kTileM - 1) / kTileM);
+      const long long ybase = (long long)b * a.y_bs, rbase = (long long)b * a.r_bs;
+      for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
+        const int abuf = ac % a.acc_bufs;
+        mbar_wait(acc_full + abuf, (ac / a.acc_bufs) & 1);
         tc_fence_after();
-        const int r = q * 32 + lane;       // accumulator row == TMEM lane
-        const int m = t0 + r;              // output row (regular) / input row (transposed)
         const int slabs = a.NT / 16;
-        for (int s = half_id; s < slabs; s += 2) {
-          uint32_t v[16];
-          __syncwarp();
-          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 16), v);
-          tmem_ld_wait();
-          const int n0 = nt * a.NT + s * 16;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int m = t0 + sub * kTileM + q * 32 + lane;  // output row (regular) / input row (transposed)
+          for (int s = half_id; s < slabs; s += 2) {
+            uint32_t v[16];
+            __syncwarp();
+            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * a.S * a.NT + sub * a.NT + s * 16), v);
+            const int n0 = nt * a.NT + s * 16;
+            // every load is issued unconditionally (clamped addresses) before anything is consumed:
+            // the memory latency is paid once per slab, not once per column
+            if (a.up == 0) {
+              const bool row_ok = m < len_out;
+              const int tcl = min(m, len_out - 1);
+              float rres[16], racc[16];
+              if (a.residual) {
+                const float* rp = a.residual + rbase + tcl;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + i;
-            if (n >= a.N_total) break;
-            int co, t;
-            if (a.up > 0) {
-              co = n / a.up;
-              t = m * a.up + (n - co * a.up) - a.up_pad;
+                for (int i = 0; i < 16; ++i) rres[i] = __ldg(rp + (long long)min(n0 + i, a.Cout - 1) * a.r_ld);
+              }
+              if (a.accumulate) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const long long yi = ybase + (long long)min(n0 + i, a.Cout - 1) * a.y_ld + tcl;
+                  racc[i] = a.y_f16 ? __half2float(reinterpret_cast<const __half*>(a.y)[yi]) : reinterpret_cast<const float*>(a.y)[yi];
+                }
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int co = min(n0 + i, a.Cout - 1);
+                float val = __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f);
+                if (a.out_act == TB200_OUT_TANH) val = tanhf(val);
+                else if (a.out_act == TB200_OUT_RELU) val = fmaxf(val, 0.f);
+                val *= a.out_alpha;
+                if (a.residual) val = fmaf(a.res_beta, rres[i], val);
+                if (a.accumulate) val += racc[i];
+                if (row_ok && n0 + i < a.N_total) store_y(a, ybase + (long long)co * a.y_ld + m, val);
+              }
             } else {
-              co = n;
-              t = m;
+              // transposed conv: column n = co*u + phase lands at t = m*u + phase - u/2
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                const int co = n / a.up;
+                const int t = m * a.up + (n - co * a.up) - a.up_pad;
+                if (n >= a.N_total || t < 0 || t >= len_out) continue;
+                float val = __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f);
+                if (a.out_act == TB200_OUT_TANH) val = tanhf(val);
+                else if (a.out_act == TB200_OUT_RELU) val = fmaxf(val, 0.f);
+                val *= a.out_alpha;
+                const long long yi = ybase + (long long)co * a.y_ld + t;
+                if (a.residual) val = fmaf(a.res_beta, __ldg(a.residual + rbase + (long long)co * a.r_ld + t), val);
+                if (a.accumulate) val += a.y_f16 ? __half2float(reinterpret_cast<const __half*>(a.y)[yi]) : reinterpret_cast<const float*>(a.y)[yi];
+                store_y(a, yi, val);
+              }
             }
-            if (t < 0 || t >= len_out) continue;
-            const long long yidx = (long long)b * a.y_bs + (long long)co * a.y_ld + t;
-            const long long ridx = (long long)b * a.r_bs + (long long)co * a.r_ld + t;
-            store_y(a, yidx, finish(__uint_as_float(v[i]), a, co, ridx, yidx));
           }
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + abuf);
       }
-      first_tile = false;
     }
   }
 
@@ -261,13 +528,64 @@ static int device_props() {
 
 int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a);  // api.cu
 
-template <typename T, bool kFast>
-static int launch_t(const ConvArgs& a, int smem_bytes, int grid, cudaStream_t stream) {
-  auto kern = conv1d_umma_kernel<T, kFast>;
-  TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+template <typename T>
+static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
+  auto kern = conv1d_umma_kernel<T>;
+  static bool configured = false;
+  if (!configured) {
+    TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    configured = true;
+  }
+  int grid = g_sm_count < a.total_tiles ? g_sm_count : a.total_tiles;  // persistent: one CTA per SM
+  if (grid < 1) grid = 1;
   kern<<<grid, kThreads, smem_bytes, stream>>>(a);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+// Choose sub-tiles per CTA tile (S), buffer counts and the channel-panel split so that everything fits
+// in shared memory / the 512 TMEM columns.
+static int plan(ConvArgs& a, int elem_bytes, int rows_max) {
+  const int span = a.R - kTileM;  // halo rows (left + right)
+  const int epc = 16 / elem_bytes;
+  const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kProdWarps * 2 * kAaScratch * 4 + 256;
+  const long long w_total = (long long)a.n_chunks * a.chunk_bytes;
+  // pass 0 insists on weights resident in shared memory (no per-tile L2 re-streaming), pass 1 allows the ring
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
+      for (int S = 4; S >= 1; S >>= 1) {
+        if (S > 1 && ((S / 2) * kTileM >= rows_max)) continue;  // tile longer than the data
+        if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < 2 * g_sm_count) continue;  // keep SMs busy
+        if (S > 1 && 2 * S * a.NT > 512) continue;              // two accumulator buffers must fit in TMEM
+        const int acc_bufs = 2 * S * a.NT <= 512 ? 2 : 1;
+        const int R = S * kTileM + span;
+        for (int n_panels = 1; n_panels <= a.n_kchunks; ++n_panels) {
+          if (a.n_kchunks % n_panels) continue;
+          const int a_bytes = (a.Cin_pad / n_panels / epc) * R * 16;
+          const long long budget = (long long)g_max_smem - fixed - (long long)a_bufs * a_bytes;
+          if (budget < 2LL * a.chunk_bytes) continue;
+          const bool resident = w_total <= budget && a.n_chunks <= kMaxRing;
+          if (pass == 0 && (!resident || n_panels > 1)) continue;
+          a.S = S; a.a_bufs = a_bufs; a.acc_bufs = acc_bufs; a.n_panels = n_panels; a.R = R; a.a_bytes = a_bytes;
+          if (resident) {
+            a.resident = 1;
+            a.ring_slots = a.n_chunks;
+          } else {
+            a.resident = 0;
+            long long slots = budget / a.chunk_bytes;
+            a.ring_slots = (int)(slots > 8 ? 8 : slots);
+          }
+          int cols = 32;
+          while (cols < acc_bufs * S * a.NT) cols <<= 1;
+          a.tmem_cols = cols;
+          a.tiles_per_utt = (rows_max + S * kTileM - 1) / (S * kTileM);
+          a.total_tiles = a.tiles_per_utt * a.B;
+          return 0;
+        }
+      }
+    }
+  }
+  return fail(TB200_E_NOSMEM, "conv1d: no tiling of Cin=%d Cout=%d taps=%d fits in shared memory", a.Cin, a.Cout, a.ntaps);
 }
 
 int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
@@ -276,30 +594,18 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   ConvArgs a;
   rc = fill_conv_args(p, p->precision, a);
   if (rc) return rc;
-
-  const int bar_bytes = (2 * 256 + 2) * 8 + 16;
-  const int scratch_bytes = kComputeWarps * 2 * kAaScratch * 4;
-  const int budget = g_max_smem - a.a_bytes - bar_bytes - scratch_bytes - 256;
-  if (budget < 2 * a.chunk_bytes) return fail(TB200_E_NOSMEM, "conv1d: input tile of %d bytes leaves no room for weight blocks", a.a_bytes);
-  if ((long long)a.n_chunks * a.chunk_bytes <= budget && a.n_chunks <= 256) {
-    a.resident = 1;
-    a.ring_slots = a.n_chunks;
-  } else {
-    a.resident = 0;
-    a.ring_slots = budget / a.chunk_bytes;
-    if (a.ring_slots > 6) a.ring_slots = 6;
-  }
-  const int smem_bytes = a.a_bytes + a.ring_slots * a.chunk_bytes + bar_bytes + scratch_bytes;
-  int grid = a.total_tiles < g_sm_count ? a.total_tiles : g_sm_count;
-  // small footprints: let two or three CTAs share an SM so one CTA's staging overlaps another's MMA
-  int per_sm = 1;
-  if (smem_bytes * 2 + 2048 <= g_max_smem && a.tmem_cols * 2 <= 512) per_sm = 2;
-  if (smem_bytes * 3 + 3072 <= g_max_smem && a.tmem_cols * 3 <= 512) per_sm = 3;
-  if (a.total_tiles > g_sm_count) grid = a.total_tiles < g_sm_count * per_sm ? a.total_tiles : g_sm_count * per_sm;
-  if (grid < 1) grid = 1;
-  const bool fast = true;
-  if (p->precision == TB200_PREC_F16) return fast ? launch_t<__half, true>(a, smem_bytes, grid, stream) : launch_t<__half, false>(a, smem_bytes, grid, stream);
-  return launch_t<float, false>(a, smem_bytes, grid, stream);
+  const int elem_bytes = p->precision == TB200_PREC_F16 ? 2 : 4;
+  const int rows_max = p->L_in_max + (a.up > 0 ? 1 : 0);
+  rc = plan(a, elem_bytes, rows_max);
+  if (rc) return rc;
+  // lane=channel snake staging: 16-byte loads need an aligned base / pitch and 32-channel blocks
+  const int align = a.x_f16 ? 8 : 4;
+  a.aa_fast = (a.act == TB200_ACT_AA_SNAKEBETA) && (a.Cin % 32 == 0) && ((a.Cin_pad / a.n_panels) % 32 == 0) &&
+              (a.x_ld % align == 0) && (a.x_bs % align == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+  const int smem_bytes = ws_layout(a).total;
+  if (smem_bytes > g_max_smem) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
+  if (p->precision == TB200_PREC_F16) return launch_t<__half>(a, smem_bytes, stream);
+  return launch_t<float>(a, smem_bytes, stream);
 }
 
 }  // namespace tb200

@@ -41,7 +41,11 @@ struct ConvArgs {
   int accumulate;
   int tiles_per_utt, total_tiles;
   int tmem_cols;
-  int a_bytes;            // staged input tile bytes
+  int a_bytes;            // bytes of one staged input buffer (one channel panel)
+  int S;                  // 128-row sub-tiles (accumulators) per CTA tile
+  int a_bufs, acc_bufs;   // staged-input / accumulator buffers (pipeline depth)
+  int n_panels;           // input-channel panels staged one at a time (1 = all channels at once)
+  int aa_fast;            // lane=channel snake staging allowed (alignment / channel-count preconditions)
 };
 
 struct ConvGeom {
@@ -62,11 +66,11 @@ inline ConvGeom conv_geom(int Cin, int Cout, int K, int up, int precision) {
   g.n_ntiles = (n16 + 255) / 256;
   g.NT = ((n16 + g.n_ntiles - 1) / g.n_ntiles + 15) / 16 * 16;
   g.ntaps = up > 0 ? 2 : K;
-  // channel chunk: largest multiple of kstep dividing Cin_pad with KC*NT*elem <= 32 KB
+  // channel chunk: largest multiple of kstep dividing Cin_pad with KC*NT*elem <= 16 KB
   int best = kstep;
   for (int kc = kstep; kc <= g.Cin_pad; kc += kstep) {
     if (g.Cin_pad % kc) continue;
-    if ((long long)kc * g.NT * g.elem_bytes <= 32768) best = kc;
+    if ((long long)kc * g.NT * g.elem_bytes <= 16384) best = kc;
   }
   g.KC = best;
   g.n_kchunks = g.Cin_pad / g.KC;
