@@ -4,6 +4,7 @@ Host code is Python/PyTorch (device memory, streams); every hot op is a hand-wri
 kernel in libtoucan_b200.so behind the C ABI of include/toucan_b200.h.  No CPU fallback.
 """
 from . import _lib, layouts, ops  # noqa: F401
+from .toucantts import ToucanTTS  # noqa: F401
 from .vocoder import BigVGAN, HiFiGANGenerator  # noqa: F401
 
-__all__ = ["BigVGAN", "HiFiGANGenerator", "ops", "layouts"]
+__all__ = ["ToucanTTS", "BigVGAN", "HiFiGANGenerator", "ops", "layouts"]

@@ -44,6 +44,26 @@ SIGNATURES = {
     "tb200_length_regulate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "tb200_channel_norm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "tb200_group_norm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p]),
+    "tb200_glu_dwconv": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "tb200_relpos_attention": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "tb200_rowvec_affine": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_int64, c_float, c_void_p]),
+    "tb200_transpose": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p]),
+    "tb200_squeeze2": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p]),
+    "tb200_wn_gate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tb200_flow_close": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tb200_l2_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tb200_cln_mlp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -4,3 +4,4 @@
 #include "conv1d_simt.cu"
 #include "conv1d_umma.cu"
 #include "ragged.cu"
+#include "acoustic.cu"

@@ -96,35 +96,36 @@ class ConvLayer:
         return out
 
 
-def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1.0, duration_scale=1.0):
-    """text (B,T,62) fp32, text_len (B) int32, log_dur (B,T) fp32 or gold_dur (B,T) int64.
-    Returns durations (B,T) int64, inclusive prefix sums (B,T) int32, frames (B) int32."""
+def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1.0, duration_scale=1.0, t_ld=None):
+    """text (B,T,62) fp32, text_len (B) int32, log_dur (B,T_ld) fp32 or gold_dur (B,T_ld) int64 (T_ld >= T, row pitch).
+    Returns durations (B,T_ld) int64, inclusive prefix sums (B,T_ld) int32, frames (B) int32."""
     global LAUNCHES
     _require_cuda(text, text_len, log_dur, gold_dur)
     b, t, _ = text.shape
     src = log_dur if log_dur is not None else gold_dur
     src = src.contiguous()
+    t_ld = src.shape[1]
     text = text.contiguous()
-    dur = torch.empty((b, t), dtype=torch.int64, device=text.device)
-    cum = torch.empty((b, t), dtype=torch.int32, device=text.device)
+    dur = torch.empty((b, t_ld), dtype=torch.int64, device=text.device)
+    cum = torch.empty((b, t_ld), dtype=torch.int32, device=text.device)
     frames = torch.empty((b,), dtype=torch.int32, device=text.device)
     _lib.check(_lib.load().tb200_duration_finalize(
-        _ptr(src) if log_dur is not None else None, _ptr(src) if log_dur is None else None, _ptr(text), _ptr(text_len), b, t, t,
+        _ptr(src) if log_dur is not None else None, _ptr(src) if log_dur is None else None, _ptr(text), _ptr(text_len), b, t, t_ld,
         float(pause_scale), float(duration_scale), _ptr(dur), _ptr(cum), _ptr(frames), _lib.stream_ptr()),
         "tb200_duration_finalize")
     LAUNCHES += 1
     return dur, cum, frames
 
 
-def variance_edit(curve, text, text_len, which, variance_scale=1.0):
-    """In-place pitch (which=0) / energy (which=1) edits + variance scaling on curve (B,T) fp32."""
+def variance_edit(curve, text, text_len, which, variance_scale=1.0, t_ld=None):
+    """In-place pitch (which=0) / energy (which=1) edits + variance scaling on curve (B,T_ld) fp32."""
     global LAUNCHES
     _require_cuda(curve, text, text_len)
     b, t, _ = text.shape
-    if not curve.is_contiguous() or curve.shape != (b, t):
-        raise _lib.EngineError("variance_edit: curve must be contiguous (B,T)")
-    _lib.check(_lib.load().tb200_variance_edit(_ptr(curve), _ptr(text.contiguous()), _ptr(text_len), b, t, t, int(which),
-                                               float(variance_scale), _lib.stream_ptr()), "tb200_variance_edit")
+    if not curve.is_contiguous() or curve.shape[0] != b or curve.shape[1] < t:
+        raise _lib.EngineError("variance_edit: curve must be contiguous (B,T_ld)")
+    _lib.check(_lib.load().tb200_variance_edit(_ptr(curve), _ptr(text.contiguous()), _ptr(text_len), b, t, curve.shape[1],
+                                               int(which), float(variance_scale), _lib.stream_ptr()), "tb200_variance_edit")
     LAUNCHES += 1
     return curve
 
@@ -145,3 +146,122 @@ def length_regulate(enc, cum, text_len, frames, f_max, pitch=None, energy=None, 
         _ptr(out), out.stride(0), out.stride(1), _ptr(f2p), f_ld, _lib.stream_ptr()), "tb200_length_regulate")
     LAUNCHES += 1
     return (out, f2p) if want_index else out
+
+
+# ---------------------------------------------------------------------------------------------
+# acoustic-model kernels (csrc/acoustic.cu).  All tensors fp32 NCL (B,C,L) with unit time stride.
+# ---------------------------------------------------------------------------------------------
+
+def _ncl(t):
+    if t.dtype != torch.float32 or t.dim() != 3 or t.stride(2) != 1:
+        raise _lib.EngineError(f"expected an fp32 NCL tensor with contiguous rows, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    return ctypes.c_void_p(t.data_ptr()), t.stride(0), t.stride(1)
+
+
+def _call(name, *args):
+    global LAUNCHES
+    _lib.check(getattr(_lib.load(), name)(*args, _lib.stream_ptr()), name)
+    LAUNCHES += 1
+
+
+def channel_norm(x, lengths, out, gamma, beta, l_max, conditional=False, eps=1e-12):
+    """LayerNorm over channels (conditional=False) or ConditionalLayerNorm with per-utterance (B,C) gamma/beta."""
+    _require_cuda(x, out, gamma, beta, lengths)
+    b, c, _ = x.shape
+    gb_bs = gamma.stride(0) if conditional else 0
+    _call("tb200_channel_norm", *_ncl(x), *_ncl(out), _ptr(lengths), b, c, int(l_max), _ptr(gamma), _ptr(beta), gb_bs,
+          1 if conditional else 0, float(eps))
+    return out
+
+
+def group_norm(x, lengths, out, gamma, beta, groups, l_max, residual=None, tanh=False, eps=1e-5):
+    _require_cuda(x, out, gamma, beta, lengths, residual)
+    b, c, _ = x.shape
+    rp = _ncl(residual) if residual is not None else (None, 0, 0)
+    _call("tb200_group_norm", *_ncl(x), *_ncl(out), *rp, _ptr(lengths), b, c, int(l_max), int(groups), _ptr(gamma), _ptr(beta),
+          float(eps), OUT_TANH if tanh else OUT_NONE)
+    return out
+
+
+def glu_dwconv(x, lengths, out, w, bias, bn_mean, bn_var, bn_gamma, bn_beta, l_max, bn_eps=1e-5):
+    _require_cuda(x, out, w, bias, lengths)
+    b, c, _ = out.shape
+    _call("tb200_glu_dwconv", *_ncl(x), *_ncl(out), _ptr(lengths), b, c, int(l_max), _ptr(w), _ptr(bias), int(w.shape[-1]),
+          _ptr(bn_mean), _ptr(bn_var), _ptr(bn_gamma), _ptr(bn_beta), float(bn_eps))
+    return out
+
+
+def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max):
+    _require_cuda(qkv, out, pos, bias_u, bias_v, lengths)
+    b, c3, _ = qkv.shape
+    dk = c3 // 3 // heads
+    _call("tb200_relpos_attention", *_ncl(qkv), _ptr(pos), pos.stride(0), int(pos_center), pos.shape[1], _ptr(bias_u),
+          _ptr(bias_v), _ptr(lengths), b, int(heads), dk, int(l_max), *_ncl(out))
+    return out
+
+
+def rowvec_affine(x, lengths, out, l_max, vec=None, scale=1.0):
+    _require_cuda(x, out, vec, lengths)
+    b, c, _ = out.shape
+    xp = _ncl(x) if x is not None else (None, 0, 0)
+    _call("tb200_rowvec_affine", *xp, *_ncl(out), _ptr(lengths), b, c, int(l_max), _ptr(vec),
+          vec.stride(0) if vec is not None else 0, float(scale))
+    return out
+
+
+def to_ncl(x_blc, lengths, out, l_max):
+    """(B,L,C) -> NCL (B,C,L)."""
+    _require_cuda(x_blc, out, lengths)
+    b, _, c = x_blc.shape
+    _call("tb200_transpose", _ptr(x_blc), x_blc.stride(0), x_blc.stride(1), *_ncl(out), _ptr(lengths), b, c, int(l_max), 1)
+    return out
+
+
+def from_ncl(x, lengths, out_blc, l_max):
+    """NCL (B,C,L) -> (B,L,C)."""
+    _require_cuda(x, out_blc, lengths)
+    b, c, _ = x.shape
+    _call("tb200_transpose", *_ncl(x), _ptr(out_blc), out_blc.stride(0), out_blc.stride(1), _ptr(lengths), b, c, int(l_max), 0)
+    return out_blc
+
+
+def squeeze2(x, lengths, out, l_max, inverse=False):
+    """Glow squeeze (inverse=False: lengths/l_max unsqueezed) or unsqueeze (inverse=True: lengths/l_max squeezed).
+    The channel count passed to the kernel is always the UNSQUEEZED one."""
+    _require_cuda(x, out, lengths)
+    b = x.shape[0]
+    c = out.shape[1] if inverse else x.shape[1]
+    _call("tb200_squeeze2", *_ncl(x), *_ncl(out), _ptr(lengths), b, c, int(l_max), 1 if inverse else 0)
+    return out
+
+
+def wn_gate(a, lengths, out, l_max):
+    _require_cuda(a, out, lengths)
+    b, h, _ = out.shape
+    _call("tb200_wn_gate", *_ncl(a), *_ncl(out), _ptr(lengths), b, h, int(l_max))
+    return out
+
+
+def flow_close(x, ml, lengths, l_max, w_inv, an_bias, an_logs):
+    _require_cuda(x, ml, lengths, w_inv, an_bias, an_logs)
+    b, c, _ = x.shape
+    _call("tb200_flow_close", *_ncl(x), *_ncl(ml), _ptr(lengths), b, c, int(l_max), _ptr(w_inv), _ptr(an_bias), _ptr(an_logs))
+    return x
+
+
+def l2_normalize(x):
+    _require_cuda(x)
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    _call("tb200_l2_normalize", _ptr(x), _ptr(y), x.shape[0], x.shape[1])
+    return y
+
+
+def cln_mlp(e, w0, b0, w2, b2, w4, b4):
+    """e (B,E); stacked MLP weights (N,...) -> (N,B,Cc)."""
+    _require_cuda(e, w0, b0, w2, b2, w4, b4)
+    n, cc = w4.shape[0], w4.shape[1]
+    out = torch.empty((n, e.shape[0], cc), dtype=torch.float32, device=e.device)
+    _call("tb200_cln_mlp", _ptr(e), e.shape[0], e.shape[1], cc, n, _ptr(w0), _ptr(b0), _ptr(w2), _ptr(b2), _ptr(w4), _ptr(b4),
+          _ptr(out))
+    return out

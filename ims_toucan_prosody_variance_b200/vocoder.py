@@ -21,6 +21,10 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
 class _GeneratorBase(torch.nn.Module):
     """Shared engine of the two generators; subclasses provide the key naming and activations."""
 
@@ -94,7 +98,8 @@ class _GeneratorBase(torch.nn.Module):
                 # value between the two convs of a residual pair: an MMA operand only -> fp16 in the
                 # fp16-operand mode, fp32 otherwise
                 tdt = torch.float16 if self.precision == "f16" else torch.float32
-                ws[f"t{i}"] = torch.zeros((b, c, _pad4(length) + 4), dtype=tdt, device=dev)
+                # row pitch a multiple of 8 elements: the lane=channel snake staging reads 16-byte groups
+                ws[f"t{i}"] = torch.zeros((b, c, _pad8(length) + 8), dtype=tdt, device=dev)
             ws["wave"] = torch.zeros((b, 1, _pad4(length)), dtype=torch.float32, device=dev)
             self._buffers_cache[key] = ws
         return ws

@@ -170,6 +170,89 @@ int tb200_length_regulate(const float* enc, int64_t enc_bs, int32_t enc_ld,
                           float* out, int64_t out_bs, int32_t out_ld,
                           int32_t* frame_to_phone, int32_t f2p_ld, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Acoustic model (ToucanTTS) -- the non-GEMM kernels.  All fp32, NCL tensors, ragged by `len`
+ * (device int32 (B) or NULL = L_max): positions >= len[b] are neither read as data nor written.
+ * ---------------------------------------------------------------------------------------- */
+
+/* LayerNorm over the channel axis (Layers/LayerNorm.py:17, eps 1e-12, biased variance) --
+ * mode 0: y = (x - mean) * rsqrt(var + eps) * gamma[c] + beta[c]
+ * or ConditionalLayerNorm (Layers/ConditionalLayerNorm.py:52-67) --
+ * mode 1: y = gamma[b][c] * (x - mean) / var + beta[b][c]   (VARIANCE, no epsilon: reference quirk).
+ * gamma/beta are (C) with gb_bs = 0, or (B, C) with batch stride gb_bs.  C <= 256.           */
+int tb200_channel_norm(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t y_bs, int32_t y_ld,
+                       const int32_t* len, int32_t B, int32_t C, int32_t L_max,
+                       const float* gamma, const float* beta, int64_t gb_bs, int32_t mode, float eps, void* stream);
+
+/* GroupNorm over (channels of a group) x (the utterance's own frames) + optional tanh + optional
+ * residual add: y = residual + OUT(gn(x) * gamma + beta)   (Layers/PostNet.py:45-59,62-74 and the
+ * `mel + postnet(mel)` of InferenceToucanTTS.py:241).  out_act: TB200_OUT_NONE | TB200_OUT_TANH.   */
+int tb200_group_norm(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t y_bs, int32_t y_ld,
+                     const float* residual, int64_t r_bs, int32_t r_ld, const int32_t* len, int32_t B, int32_t C,
+                     int32_t L_max, int32_t groups, const float* gamma, const float* beta, float eps, int32_t out_act,
+                     void* stream);
+
+/* Middle of the Conformer convolution module (Layers/Convolution.py:43-52): GLU over channels of
+ * x (B, 2C, L), depthwise Conv1d (C, K) zero padded at the utterance's own ends + bias, eval-mode
+ * BatchNorm1d ((h - mean) * rsqrt(var + eps) * gamma + beta), Swish.  y (B, C, L).  K odd, <= 63. */
+int tb200_glu_dwconv(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t y_bs, int32_t y_ld,
+                     const int32_t* len, int32_t B, int32_t C, int32_t L_max, const float* w, const float* bias, int32_t K,
+                     const float* bn_mean, const float* bn_var, const float* bn_gamma, const float* bn_beta, float bn_eps,
+                     void* stream);
+
+/* Relative-position multi-head attention core (Layers/Attention.py:159-198 with rel_shift :138-157
+ * and forward_attention :66-92), flash style (no (T, 2T-1) score tensor):
+ *   score(i,j) = ((q_i + u_h) . k_j + (q_i + v_h) . p_{i-j}) / sqrt(dk)  for j < len[b];
+ *   out_i = sum_j softmax_j(score(i, .)) v_j.
+ * qkv (B, 3*H*dk, L): rows [0,D) q, [D,2D) k, [2D,3D) v (D = H*dk, head h = rows h*dk..);
+ * pos (D, pos_cols): column (pos_center - r) holds linear_pos(PE(r)) for relative position r;
+ * bias_u / bias_v (H, dk); out (B, D, L).  dk in {32, 48, 64}.                                  */
+int tb200_relpos_attention(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const float* pos, int32_t pos_ld,
+                           int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v,
+                           const int32_t* len, int32_t B, int32_t H, int32_t dk, int32_t L_max,
+                           float* out, int64_t out_bs, int32_t out_ld, void* stream);
+
+/* y[b][c][t] = (x[b][c][t] + vec[b][c]) * scale; x or vec may be NULL (treated as 0).  Covers the
+ * language-embedding add and the sqrt(adim) scale of RelPositionalEncoding (Conformer.py:108-118,
+ * PositionalEncoding.py:119-130) and the broadcast of the utterance embedding that
+ * Conformer.py:131-134 concatenates to the encoder output.                                      */
+int tb200_rowvec_affine(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t y_bs, int32_t y_ld,
+                        const int32_t* len, int32_t B, int32_t C, int32_t L_max, const float* vec, int64_t vec_bs,
+                        float scale, void* stream);
+
+/* (B, L, C) row-major <-> NCL (B, C, L).  to_ncl != 0: in is (B,L,C) with row pitch in_ld, out NCL;
+ * else in is NCL and out (B,L,C) (the reference's module-boundary layout).                       */
+int tb200_transpose(const float* in, int64_t in_bs, int32_t in_ld, float* out, int64_t out_bs, int32_t out_ld,
+                    const int32_t* len, int32_t B, int32_t C, int32_t L_max, int32_t to_ncl, void* stream);
+
+/* Glow squeeze / unsqueeze with n_sqz = 2 (ToucanTTS/glow_utils.py:28-53).
+ * inverse == 0: x (B,C,L) -> y (B,2C,L/2), y[s*C+c][tau] = x[c][2tau+s]; len = unsqueezed lengths
+ * (an odd last frame is dropped).  inverse != 0: x (B,2C,L2) -> y (B,C,2*L2); len = squeezed.     */
+int tb200_squeeze2(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t y_bs, int32_t y_ld,
+                   const int32_t* len, int32_t B, int32_t C, int32_t L_max, int32_t inverse, void* stream);
+
+/* WaveNet gate (ToucanTTS/wavenet.py:29-35,102-111): y[c] = tanh(a[c]) * sigmoid(a[c + hidden]);
+ * a (B, 2*hidden, L), y (B, hidden, L).                                                          */
+int tb200_wn_gate(const float* a, int64_t a_bs, int32_t a_ld, float* y, int64_t y_bs, int32_t y_ld,
+                  const int32_t* len, int32_t B, int32_t hidden, int32_t L_max, void* stream);
+
+/* Closes one reversed flow block in place on x (B, C, L) (ToucanTTS/Glow.py:260-263, 116-128, 30-32):
+ * coupling^-1  x[C/2:] = (x[C/2:] - ml[:C/2]) * exp(-ml[C/2:]);  invconv^-1 with the cached 4x4
+ * inverse w_inv (row-major) over the channel groups of InvConvNear; actnorm^-1
+ * (x - an_bias[c]) * exp(-an_logs[c]).                                                           */
+int tb200_flow_close(float* x, int64_t x_bs, int32_t x_ld, const float* ml, int64_t ml_bs, int32_t ml_ld,
+                     const int32_t* len, int32_t B, int32_t C, int32_t L_max, const float* w_inv,
+                     const float* an_bias, const float* an_logs, void* stream);
+
+/* torch.nn.functional.normalize on (B, C) rows (InferenceToucanTTS.py:202, Conformer.py:132).     */
+int tb200_l2_normalize(const float* x, float* y, int32_t B, int32_t C, void* stream);
+
+/* The N stacked conditioning MLPs of ConditionalLayerNorm (ConditionalLayerNorm.py:27-50):
+ * out[n][b] = W4_n tanh(W2_n tanh(W0_n e_b + b0_n) + b2_n) + b4_n;  e (B,E); w0 (N,E,E), w2 (N,Cc,E),
+ * w4 (N,Cc,Cc) in torch Linear layout (out, in); out (N, B, Cc).                                  */
+int tb200_cln_mlp(const float* e, int32_t B, int32_t E, int32_t Cc, int32_t N, const float* w0, const float* b0,
+                  const float* w2, const float* b2, const float* w4, const float* b4, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

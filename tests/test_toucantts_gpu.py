@@ -1,0 +1,166 @@
+"""ToucanTTS acoustic model on the GPU against the oracle (stage by stage), the golden fixtures of the
+live reference, and batch-vs-single consistency.
+
+Tolerances (north_star): integer durations and frame counts bit-exact; mel relative L1 <= 1e-3 in the
+fp32-accumulate modes ("fp32" = CUDA-core fp32, "tf32" = tcgen05 kind::tf32 with fp32 accumulation in TMEM);
+the fp16-operand mode is the looser-bound mode (<= 1e-2)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MEL_TOL = {"fp32": 1e-3, "tf32": 1e-3, "f16": 1e-2}
+_ENGINES = {}
+
+
+def _engine(cuda, prec):
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory, restate
+    if prec not in _ENGINES:
+        sd = factory.make_state_dict("toucantts", 1234)
+        model = tb.ToucanTTS(weights=sd, precision=prec).to(cuda)
+        model.store_inverse_all()
+        _ENGINES[prec] = (model, restate.fold_weight_norm(sd))
+    return _ENGINES[prec]
+
+
+def _rel_l1(a, b):
+    return ((a - b).abs().mean() / b.abs().mean().clamp_min(1e-12)).item()
+
+
+def _log(lines):
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "toucantts_stage_errors.txt"), "a") as f:
+            f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
+def test_stagewise_vs_oracle(cuda, prec):
+    from oracle import factory, restate
+    model, fsd = _engine(cuda, prec)
+    n_ph, seed = 23, 5
+    text = factory.make_phoneme_tensor(n_ph, seed)
+    emb = factory.make_utterance_embedding(seed)
+    otaps = {}
+    with torch.inference_mode():
+        ref = restate.toucantts_forward(fsd, text, emb, lang_id=12, generator=torch.Generator().manual_seed(99), taps=otaps)
+    frames = int(ref["durations"].sum())
+    noise = torch.randn((1, 80, frames), generator=torch.Generator().manual_seed(99))
+
+    taps = {}
+    r = model.synthesize_batch(text.unsqueeze(0).to(cuda), torch.tensor([n_ph]), utterance_embedding=emb.unsqueeze(0).to(cuda),
+                               lang_ids=torch.tensor([12]), noise=noise, taps=taps)
+    torch.cuda.synchronize()
+    lines = [f"== stagewise {prec}: {n_ph} phonemes, {frames} frames"]
+    enc_err = _rel_l1(taps["encoder"][0, :, :n_ph].t().cpu(), otaps["encoder"])
+    lines.append(f"encoder rel-L1 {enc_err:.3e}")
+    lines.append(f"log-durations max abs err {(r['log_durations'][0, :n_ph].cpu() - ref['log_durations']).abs().max().item():.3e}")
+    lines.append(f"pitch rel-L1 {_rel_l1(r['pitch'][0, :n_ph].cpu(), ref['pitch']):.3e}  energy rel-L1 "
+                 f"{_rel_l1(r['energy'][0, :n_ph].cpu(), ref['energy']):.3e}")
+    dur_equal = torch.equal(r["durations"][0, :n_ph].cpu(), ref["durations"])
+    lines.append(f"durations equal: {dur_equal}  frames engine {int(r['frames'][0])} oracle {frames}")
+    errs = {}
+    if dur_equal:
+        for name, key in (("upsampled", "upsampled"), ("decoder", "decoder"), ("decoded", "decoded"), ("refined", "refined")):
+            errs[name] = _rel_l1(taps[name][0, :, :frames].t().cpu(), otaps[key])
+            lines.append(f"{name} rel-L1 {errs[name]:.3e}")
+        for i, xb in enumerate(taps["flow_blocks"]):
+            b = 17 - i
+            e = _rel_l1(xb[0, :, :frames // 2].cpu(), otaps[f"post_flow.block{b}"])
+            if i % 6 == 5 or i == 0:
+                lines.append(f"flow block {b} rel-L1 {e:.3e}")
+        m = 2 * (frames // 2)
+        errs["mel"] = _rel_l1(r["mel_ncl"][0, :, :m].t().cpu(), ref["mel"])
+        lines.append(f"mel rel-L1 {errs['mel']:.3e}  (bound {MEL_TOL[prec]:.0e})")
+    _log(lines)
+    assert int(r["frames"][0]) == int(r["durations"][0, :n_ph].sum())
+    if prec == "fp32":
+        assert dur_equal, "fp32 mode must reproduce the oracle's integer durations"
+    if dur_equal:
+        assert enc_err < (1e-4 if prec == "fp32" else 5e-3)
+        assert errs["upsampled"] < (1e-4 if prec == "fp32" else 5e-3)
+        assert errs["mel"] <= MEL_TOL[prec], f"mel rel-L1 {errs['mel']:.3e}"
+    else:
+        pytest.fail(f"{prec}: durations differ from the oracle's (see gpurun_out/toucantts_stage_errors.txt)")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_golden_fixture_cases(cuda, prec):
+    """Outputs of the reference's unmodified InferenceToucanTTS (tests/golden/toucantts.pt, oracle/make_golden.py):
+    predicted prosody, scaled prosody, external (cloner-shaped) prosody; noise from the global CPU generator."""
+    from oracle import factory
+    model, _ = _engine(cuda, prec)
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "toucantts.pt"))
+    lines = [f"== golden {prec}"]
+    failures = []
+    for case in gold["cases"]:
+        text = factory.make_phoneme_tensor(case["n_ph"], case["seed"])
+        emb = factory.make_utterance_embedding(case["seed"])
+        args = {}
+        if case["gold"]:
+            d, p, e = factory.make_gold_prosody(text, case["seed"])
+            args = dict(durations=d.clone(), pitch=p.clone(), energy=e.clone())
+        torch.manual_seed(case["noise_seed"])
+        mel, dur, pitch, energy = model(text.to(cuda), utterance_embedding=emb.to(cuda), lang_id=torch.tensor([gold["lang_id"]]).to(cuda),
+                                        return_duration_pitch_energy=True, **args, **case["kw"])
+        dur_ok = torch.equal(dur.cpu(), case["durations"])
+        line = f"case n_ph={case['n_ph']} gold={case['gold']} kw={case['kw']}: durations equal {dur_ok}"
+        if dur_ok:
+            err = _rel_l1(mel.cpu(), case["mel"])
+            line += (f" mel rel-L1 {err:.3e} pitch {_rel_l1(pitch.cpu(), case['pitch']):.3e} "
+                     f"energy {_rel_l1(energy.cpu(), case['energy']):.3e}")
+            if err > MEL_TOL[prec]:
+                failures.append(line)
+        else:
+            failures.append(line)
+        lines.append(line)
+    _log(lines)
+    assert not failures, failures
+
+
+def test_ragged_batch_equals_single_calls(cuda):
+    """A ragged batch must equal per-utterance batch-1 calls (no leakage through conv halos, attention, norms)."""
+    from oracle import factory
+    model, _ = _engine(cuda, "tf32")
+    lens = [31, 12, 20]
+    texts = [factory.make_phoneme_tensor(n, 40 + i) for i, n in enumerate(lens)]
+    embs = torch.stack([factory.make_utterance_embedding(40 + i) for i in range(len(lens))])
+    batch = torch.zeros(len(lens), max(lens), 62)
+    for i, t in enumerate(texts):
+        batch[i, :lens[i]] = t
+    noise = torch.randn(len(lens), 80, 600, generator=torch.Generator().manual_seed(3))
+    rb = model.synthesize_batch(batch.to(cuda), torch.tensor(lens), utterance_embedding=embs.to(cuda),
+                                lang_ids=torch.tensor([12, 12, 12]), noise=noise)
+    for i, n in enumerate(lens):
+        rs = model.synthesize_batch(texts[i].unsqueeze(0).to(cuda), torch.tensor([n]), utterance_embedding=embs[i:i + 1].to(cuda),
+                                    lang_ids=torch.tensor([12]), noise=noise[i:i + 1])
+        assert torch.equal(rb["durations"][i, :n].cpu(), rs["durations"][0, :n].cpu())
+        m = int(rs["mel_lengths"][0])
+        assert int(rb["mel_lengths"][i]) == m
+        a, b = rb["mel_ncl"][i, :, :m].cpu(), rs["mel_ncl"][0, :, :m].cpu()
+        assert _rel_l1(a, b) < 1e-5, f"utterance {i}: batch vs single rel-L1 {_rel_l1(a, b):.3e}"
+
+
+def test_long_form_external_prosody(cuda):
+    """Config-5 shaped input at reduced length: 400 phonemes with external durations/pitch/energy (UtteranceCloner
+    override path, InferenceToucanTTS.py:204-212): frames = sum(edited durations), output finite."""
+    from oracle import factory, restate
+    model, _ = _engine(cuda, "tf32")
+    n_ph = 400
+    text = factory.make_phoneme_tensor(n_ph, 9)
+    emb = factory.make_utterance_embedding(9)
+    d, p, e = factory.make_gold_prosody(text, 9)
+    ref_d, ref_p, ref_e = restate.edit_prosody(text, d, p.reshape(-1), e.reshape(-1), 1.2, 1.1, 1.2, 0.8)
+    mel, dur, pitch, energy = model(text.to(cuda), durations=d.clone(), pitch=p.clone(), energy=e.clone(),
+                                    utterance_embedding=emb.to(cuda), lang_id=torch.tensor([12]).to(cuda),
+                                    return_duration_pitch_energy=True, duration_scaling_factor=1.1,
+                                    pause_duration_scaling_factor=1.2, pitch_variance_scale=1.2, energy_variance_scale=0.8)
+    assert torch.equal(dur.cpu(), ref_d)
+    assert torch.allclose(pitch.cpu(), ref_p, atol=1e-5) and torch.allclose(energy.cpu(), ref_e, atol=1e-5)
+    assert mel.shape == (2 * (int(ref_d.sum()) // 2), 80)
+    assert torch.isfinite(mel).all()
