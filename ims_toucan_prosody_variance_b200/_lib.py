@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtoucan_b200.so")
+LIB_PATH = os.environ.get("TB200_LIB", os.path.join(_HERE, "libtoucan_b200.so"))  # TB200_LIB: tuning builds only
 
 F32, F16 = 0, 1
 PREC_FP32_SIMT, PREC_F16, PREC_TF32 = 0, 1, 2

@@ -15,28 +15,37 @@
 //   D: fp32 in TMEM, double buffered; epilogue = tcgen05.ld -> bias / activation / scale / residual /
 //     accumulate -> coalesced NCL stores (a warp writes 32 consecutive time steps of one channel).
 //
-// Warp roles (one persistent CTA per SM, 18 warps):
-//   warps 0-7   producers : stage A[buf] (double buffered), arrive a_full
-//   warp  8     MMA issuer: one elected thread issues tcgen05.mma, commits to a_empty / acc_full / w_empty
-//   warp  9     weight loader (TMA bulk copies)
-//   warps 10-17 epilogue  : drain accumulator buffer, arrive acc_empty
+// Warp roles (one persistent CTA per SM, 16 warps = 4 per SM sub-partition, 128 registers each):
+//   warps 0 .. nP-1   producers : stage A[buf] (double buffered), arrive a_full
+//   warps nP .. 13    epilogue  : drain accumulator buffer, arrive acc_empty  (4 or 8 warps; any 4 consecutive
+//                                 warps cover the four TMEM lane quarters)
+//   warp  14          MMA issuer: one elected thread issues tcgen05.mma, commits to a_empty / acc_full / w_empty
+//   warp  15          weight loader (TMA bulk copies)
+// nP = 10 when the prologue is the anti-aliased snake (staging is the SIMT-heavy side), 6 otherwise.
 // so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 //
 // Tiles past an utterance's length are skipped, rows past it are staged as zeros (the zero padding a
 // batch-1 reference call sees).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "conv_common.cuh"
 
+#ifndef TB200_ROLE_INLINE
+#define TB200_ROLE_INLINE __forceinline__
+#endif
+#ifndef TB200_MAX_S
+#define TB200_MAX_S 8
+#endif
+
 namespace tb200 {
 
-constexpr int kProdWarps = 8;
-constexpr int kEpiWarps = 8;
-constexpr int kMmaWarp = kProdWarps;
-constexpr int kLoadWarp = kProdWarps + 1;
-constexpr int kEpiWarp0 = kProdWarps + 2;
-constexpr int kThreads = (kProdWarps + 2 + kEpiWarps) * 32;  // 576
+constexpr int kWorkerWarps = 14;           // producers [0, a.n_prod) + epilogue [a.n_prod, 14): split chosen per launch
+constexpr int kMmaWarp = kWorkerWarps;
+constexpr int kLoadWarp = kWorkerWarps + 1;
+constexpr int kThreads = (kWorkerWarps + 2) * 32;  // 512: 4 warps per SM sub-partition -> 128 registers per thread
+constexpr int kMaxProdWarps = 10;
 constexpr int kMaxRing = 64;
 
 template <typename T>
@@ -51,6 +60,8 @@ struct ElemTraits<float> {
   static constexpr int kEpc = 4;
   static constexpr bool kTf32 = true;
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -96,8 +107,9 @@ struct UmmaStore {
 // clamped addresses, the next task's loads in flight while the current one is converted/stored.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void stage_pointwise_mlp(const ConvArgs& a, int b, int t_lo, int g0, int ng, int len, T* smA,
+__device__ TB200_ROLE_INLINE void stage_pointwise_mlp(const ConvArgs& a, int b, int t_lo, int g0, int ng, int len, T* smA,
                                                     int pw, int lane) {
+  const int kProdWarps = a.n_prod;
   constexpr int E = ElemTraits<T>::kEpc;
   const int R = a.R;
   const int nrb = (R + 31) / 32;
@@ -135,6 +147,163 @@ __device__ __forceinline__ void stage_pointwise_mlp(const ConvArgs& a, int b, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// producer, pointwise activations, vectorised: a lane owns V consecutive time steps (one 16-byte
+// load per channel: V = 4 fp32 / 8 fp16) of the E channels of one 16-byte operand group, so a warp
+// reads 512 contiguous bytes per channel row and a thread keeps E x 16 bytes in flight (x2 with the
+// next task prefetched): ~3 instructions per element instead of ~15 for the scalar path.
+// Loads start at a 16-byte aligned time index t_al <= t_lo; vectors entirely outside [0, len) are
+// not loaded (zeros), elements past len inside the last vector are masked.
+// Preconditions (host: a.pw_vec): x base 16-byte aligned, x_ld and x_bs multiples of V.
+// ---------------------------------------------------------------------------------------------
+struct Vec16 {
+  uint4 u;
+};
+
+__device__ __forceinline__ uint32_t act_half2(uint32_t v, int act, __half2 slope2) {
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  if (act == TB200_ACT_LEAKY_RELU) h = __hmax2(h, __hmul2(h, slope2));
+  else if (act == TB200_ACT_RELU) h = __hmax2(h, __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T, bool XF16>
+__device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, int t_lo, int g0, int ng, int len, T* smA,
+                                                    int pw, int lane) {
+  const int kProdWarps = a.n_prod;
+  constexpr int E = ElemTraits<T>::kEpc;
+  constexpr int V = XF16 ? 8 : 4;   // time steps per 16-byte load
+  constexpr int CH = 4;             // channels per task: half (fp16 operands) or all (tf32) of a 16-byte operand group
+  constexpr int SUB = E / CH;
+  static_assert(!(XF16 && E != 8), "fp16 activations feed fp16 operands only");
+  const int R = a.R;
+  const int shift = ((t_lo % V) + V) % V;       // t_lo - t_al
+  const int t_al = t_lo - shift;
+  const int nq = (R + shift + V - 1) / V;
+  const int nqb = (nq + 31) / 32;
+  const int ntask = ng * SUB * nqb;
+  const long long xb = (long long)b * a.x_bs;
+  const bool simple_act = a.act == TB200_ACT_NONE || a.act == TB200_ACT_LEAKY_RELU || a.act == TB200_ACT_RELU;
+  const __half2 slope2 = __float2half2_rn(a.slope);
+  uint4 bufa[CH], bufb[CH], bufc[CH];
+  auto issue = [&](int task, uint4 (&v)[CH]) {
+    const int gs = task / nqb, q = (task - gs * nqb) * 32 + lane;
+    const int tq = t_al + V * q;
+    const bool ok = q < nq && tq >= 0 && tq < len;
+#pragma unroll
+    for (int e = 0; e < CH; ++e) {
+      const int c = g0 * E + gs * CH + e;
+      if (ok && c < a.Cin) {
+        const long long idx = xb + (long long)c * a.x_ld + tq;
+        v[e] = XF16 ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + idx))
+                    : __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.x) + idx));
+      } else {
+        v[e] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  auto process = [&](int task, uint4 (&cur)[CH]) {
+    const int gs = task / nqb, q = (task - gs * nqb) * 32 + lane;
+    const int g = gs / SUB, sub = gs - g * SUB;
+    const int tq = t_al + V * q;
+    const int r0 = V * q - shift;
+    if (q < nq) {
+      T* dst = smA + ((long long)g * R + r0) * E + sub * CH;   // row r0 of this task's CH channels
+      const bool full = tq >= 0 && tq + V <= len;
+      if constexpr (XF16) {
+        if (full && simple_act) {
+          // 8 (time) x 4 (channel) halves: activation on time pairs, then a register transpose
+#pragma unroll
+          for (int e = 0; e < CH; ++e) {
+            cur[e].x = act_half2(cur[e].x, a.act, slope2);
+            cur[e].y = act_half2(cur[e].y, a.act, slope2);
+            cur[e].z = act_half2(cur[e].z, a.act, slope2);
+            cur[e].w = act_half2(cur[e].w, a.act, slope2);
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int r = r0 + i;
+            const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+            auto word = [&](int e) { return (i >> 1) == 0 ? cur[e].x : (i >> 1) == 1 ? cur[e].y : (i >> 1) == 2 ? cur[e].z : cur[e].w; };
+            uint2 o;
+            o.x = __byte_perm(word(0), word(1), sel);
+            o.y = __byte_perm(word(2), word(3), sel);
+            if (r >= 0 && r < R) *reinterpret_cast<uint2*>(dst + (long long)i * E) = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int r = r0 + i, t = tq + i;
+            const bool valid = t >= 0 && t < len;
+            float v[CH];
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+              const uint32_t word = (i >> 1) == 0 ? cur[e].x : (i >> 1) == 1 ? cur[e].y : (i >> 1) == 2 ? cur[e].z : cur[e].w;
+              const __half2 h2 = *reinterpret_cast<const __half2*>(&word);
+              const float xv = (i & 1) ? __high2float(h2) : __low2float(h2);
+              v[e] = valid ? apply_pointwise(xv, a.act, a.slope) : 0.f;
+            }
+            if (r >= 0 && r < R) {
+              const __half2 h0 = __floats2half2_rn(clamp_f16(v[0]), clamp_f16(v[1]));
+              const __half2 h1 = __floats2half2_rn(clamp_f16(v[2]), clamp_f16(v[3]));
+              uint2 o;
+              o.x = *reinterpret_cast<const uint32_t*>(&h0);
+              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(dst + (long long)i * E) = o;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const int r = r0 + i, t = tq + i;
+          const bool valid = full || (t >= 0 && t < len);
+          float v[CH];
+#pragma unroll
+          for (int e = 0; e < CH; ++e) {
+            const uint32_t word = i == 0 ? cur[e].x : i == 1 ? cur[e].y : i == 2 ? cur[e].z : cur[e].w;
+            const float xv = valid ? __uint_as_float(word) : 0.f;   // every supported activation maps 0 -> 0
+            if (a.act == TB200_ACT_LEAKY_RELU) v[e] = fmaxf(xv, xv * a.slope);   // 0 <= slope <= 1 (checked on the host)
+            else if (a.act == TB200_ACT_NONE) v[e] = xv;
+            else v[e] = apply_pointwise(xv, a.act, a.slope);
+          }
+          if (r >= 0 && r < R) {
+            if constexpr (E == 8) {
+              const __half2 h0 = __floats2half2_rn(clamp_f16(v[0]), clamp_f16(v[1]));
+              const __half2 h1 = __floats2half2_rn(clamp_f16(v[2]), clamp_f16(v[3]));
+              uint2 o;
+              o.x = *reinterpret_cast<const uint32_t*>(&h0);
+              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(dst + (long long)i * E) = o;
+            } else {
+              *reinterpret_cast<float4*>(dst + (long long)i * E) =
+                  make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+            }
+          }
+        }
+      }
+    }
+  };
+  // three register sets rotate between "in flight" (two tasks ahead) and "being converted": no copies at the loop edge
+  int task = pw;
+  const int P = kProdWarps;
+  if (task < ntask) issue(task, bufa);
+  if (task + P < ntask) issue(task + P, bufb);
+  while (task < ntask) {
+    if (task + 2 * P < ntask) issue(task + 2 * P, bufc);
+    process(task, bufa);
+    task += P;
+    if (task >= ntask) break;
+    if (task + 2 * P < ntask) issue(task + 2 * P, bufa);
+    process(task, bufb);
+    task += P;
+    if (task >= ntask) break;
+    if (task + 2 * P < ntask) issue(task + 2 * P, bufb);
+    process(task, bufc);
+    task += P;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // producer, anti-aliased SnakeBeta, interior tiles: lane = channel, sequential in time with register
 // sliding windows (8 inputs, 8 (s_even, s_odd) pairs) -> one 16-byte load per 4 (fp32) / 8 (fp16)
 // steps per lane, 24 filter FMAs + 2 sin per output, no scratch, no intra-warp exchange.
@@ -161,13 +330,13 @@ __device__ __forceinline__ void load8(const void* x, bool f16, long long idx, fl
 }
 
 template <typename T>
-__device__ __forceinline__ void stage_aa_channel(const ConvArgs& a, int b, int t_lo, int cb0, int ncb, int nseg, T* smA,
+__device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int t_lo, int cb0, int ncb, int nseg, T* smA,
                                                  int pw, int lane) {
   constexpr int E = ElemTraits<T>::kEpc;
   const int R = a.R;
   const int seg_rows = (R + nseg - 1) / nseg;
   const long long xb = (long long)b * a.x_bs;
-  for (int task = pw; task < ncb * nseg; task += kProdWarps) {
+  for (int task = pw; task < ncb * nseg; task += a.n_prod) {
     const int cb = task / nseg, seg = task - cb * nseg;
     const int r_beg = seg * seg_rows;
     const int r_end = min(R, r_beg + seg_rows);
@@ -188,13 +357,14 @@ __device__ __forceinline__ void stage_aa_channel(const ConvArgs& a, int b, int t
     for (int i = 0; i < 16; ++i) sv[i] = 0.f;
     load8(a.x, a.x_f16, row + ts, cur);
     load8(a.x, a.x_f16, row + ts + 8, n1);
-    for (int base = ts; base - 6 < t_end; base += 8) {
-      load8(a.x, a.x_f16, row + base + 16, n2);  // look-ahead stays inside the utterance: see `interior`
+    // one 8-step block; CHECK = false once every step both produces a pair and emits an output row
+    auto block8 = [&](auto check_tag, int base) {
+      constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = base + j;
         xw[j] = cur[j];
-        if (n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
+        if (!CHECK || n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
           float u0 = 0.f, u1 = 0.f;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
@@ -208,7 +378,7 @@ __device__ __forceinline__ void stage_aa_channel(const ConvArgs& a, int b, int t
           sv[2 * ((j + 5) & 7) + 1] = fmaf(ib * z1, z1, u1);
         }
         const int t = n - 6;
-        if (t >= t_beg && t < t_end) {
+        if (!CHECK || (t >= t_beg && t < t_end)) {
           float o0 = 0.f, o1 = 0.f;
 #pragma unroll
           for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
@@ -218,6 +388,11 @@ __device__ __forceinline__ void stage_aa_channel(const ConvArgs& a, int b, int t
           dst[(long long)(t - t_lo) * E] = to_operand<T>(o0 + o1);
         }
       }
+    };
+    for (int base = ts; base - 6 < t_end; base += 8) {
+      load8(a.x, a.x_f16, row + base + 16, n2);  // look-ahead stays inside the utterance: see `interior`
+      if (base - 6 >= t_beg && base + 1 < t_end) block8(std::false_type{}, base);
+      else block8(std::true_type{}, base);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         cur[i] = n1[i];
@@ -241,11 +416,152 @@ __host__ __device__ inline WsLayout ws_layout(const ConvArgs& a) {
   const int nbars = 2 * a.ring_slots + 2 * a.a_bufs + 2 * a.acc_bufs;
   l.tmem_off = l.bar_off + nbars * 8;
   l.scratch_off = l.tmem_off + 16;
-  l.total = l.scratch_off + kProdWarps * 2 * kAaScratch * 4;
+  l.total = l.scratch_off + kMaxProdWarps * 2 * kAaScratch * 4;
   return l;
 }
 
-template <typename T>
+// ---------------------------------------------------------------------------------------------
+// epilogue bodies.  A warp owns TMEM lanes [32q, 32q+32) = 32 consecutive output rows (time steps) and
+// walks 16-column (channel) slabs: one tcgen05.ld per slab, then for each column a 128-byte coalesced
+// row of 32 time steps.  All global loads of a slab (residual / accumulate / bias) are issued before
+// the TMEM load is waited on, so their latency is paid once per slab.
+// ---------------------------------------------------------------------------------------------
+struct EpiAux {           // the one auxiliary input of the plain epilogue: residual (fp32) or the old y (accumulate)
+  const void* ptr;
+  uint32_t base;          // element offset of this utterance
+  uint32_t ld;
+  int f16;
+  float beta;
+};
+
+// Plain epilogue: regular conv, N_total % 16 == 0, no output activation, NAUX auxiliary inputs (residual and/or
+// the old y), and every tensor small enough for 32-bit element offsets (host: a.epi_fast).  Addresses are
+// (uniform 64-bit base) + (32-bit offset), one integer add per access.
+template <int NAUX>
+__device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux& ax0, const EpiAux& ax1, uint32_t tm0,
+                                                 int nsub, int slabs, int slab0, int slab_step, int nt, int m_base,
+                                                 int len_out, uint32_t ybase) {
+  // work items = (slab, sub-tile) pairs, slab-major.  The auxiliary rows of the next item(s) are requested
+  // before item k is finished (rotating register sets), so a warp keeps 32 row loads (4 KB) in flight.
+  const int nsl = (slabs - slab0 + slab_step - 1) / slab_step;
+  const int nitems = nsl * nsub;
+  float* yf = reinterpret_cast<float*>(a.y);
+  __half* yh = reinterpret_cast<__half*>(a.y);
+  const uint32_t y_ld = (uint32_t)a.y_ld;
+  auto fetch1 = [&](int k, const EpiAux& ax, float (&r)[16]) {
+    const int sl = k / nsub, sub = k - sl * nsub;
+    const uint32_t n0 = (uint32_t)(nt * a.NT + (slab0 + sl * slab_step) * 16);
+    uint32_t off = ax.base + n0 * ax.ld + (uint32_t)min(m_base + sub * kTileM, len_out - 1);
+    if (ax.f16) {
+      const __half* p = reinterpret_cast<const __half*>(ax.ptr);
+#pragma unroll
+      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = __half2float(p[off]);
+    } else {
+      const float* p = reinterpret_cast<const float*>(ax.ptr);
+#pragma unroll
+      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = p[off];
+    }
+  };
+  float bias[16];   // bias * out_alpha
+  auto finish_item = [&](int k, const float (&r0)[16], const float (&r1)[16]) {
+    const int sl = k / nsub, sub = k - sl * nsub;
+    const int s = slab0 + sl * slab_step;
+    const uint32_t n0 = (uint32_t)(nt * a.NT + s * 16);
+    if (sub == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias[i] = a.bias ? __ldg(a.bias + n0 + i) * a.out_alpha : 0.f;
+    }
+    const int m = m_base + sub * kTileM;
+    const bool row_ok = m < len_out;
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld_x16(tm0 + (uint32_t)(sub * a.NT + s * 16), v);
+    tmem_ld_wait();
+    uint32_t yo = ybase + n0 * y_ld + (uint32_t)m;
+#pragma unroll
+    for (int i = 0; i < 16; ++i, yo += y_ld) {
+      float val = fmaf(__uint_as_float(v[i]), a.out_alpha, bias[i]);
+      if constexpr (NAUX >= 1) val = fmaf(ax0.beta, r0[i], val);
+      if constexpr (NAUX >= 2) val = fmaf(ax1.beta, r1[i], val);
+      if (row_ok) {
+        if (a.y_f16) yh[yo] = __float2half_rn(clamp_f16(val));
+        else yf[yo] = val;
+      }
+    }
+  };
+  float ra[16], rb[16];
+  if constexpr (NAUX == 1) {
+    // two register sets: the rows of item k+1 are in flight while item k is finished
+    int k = 0;
+    if (k < nitems) fetch1(k, ax0, ra);
+    while (k < nitems) {
+      if (k + 1 < nitems) fetch1(k + 1, ax0, rb);
+      finish_item(k, ra, ra);
+      if (++k >= nitems) break;
+      if (k + 1 < nitems) fetch1(k + 1, ax0, ra);
+      finish_item(k, rb, rb);
+      ++k;
+    }
+  } else if constexpr (NAUX == 2) {
+    // two inputs (rare: last pair of the 2nd/3rd residual block of a stage): 32 loads per item, no look-ahead
+    for (int k = 0; k < nitems; ++k) {
+      fetch1(k, ax0, ra);
+      fetch1(k, ax1, rb);
+      finish_item(k, ra, rb);
+    }
+  } else {
+    for (int k = 0; k < nitems; ++k) finish_item(k, ra, ra);
+  }
+}
+
+// every other combination (transposed conv scatter, tanh / relu outputs)
+__device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t tm0, int nsub, int slabs, int slab0,
+                                                   int slab_step, int nt, int m_base, int len_out, long long ybase,
+                                                   long long rbase) {
+  const bool plain_out = !a.residual && !a.accumulate && a.out_act == TB200_OUT_NONE;
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int m = m_base + sub * kTileM;  // output row (regular) / input row (transposed)
+    for (int s = slab0; s < slabs; s += slab_step) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld_x16(tm0 + (uint32_t)(sub * a.NT + s * 16), v);
+      const int n0 = nt * a.NT + s * 16;
+      tmem_ld_wait();
+      if (a.up == 0) {
+        if (m >= len_out) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int co = n0 + i;
+          if (co >= a.N_total) continue;
+          const long long yi = ybase + (long long)co * a.y_ld + m;
+          store_y(a, yi, finish(__uint_as_float(v[i]), a, co, rbase + (long long)co * a.r_ld + m, yi));
+        }
+      } else {
+        // transposed conv: column n = co*u + phase lands at t = m*u + phase - u/2
+        const int t_first = m * a.up - a.up_pad;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + i;
+          const int co = n / a.up;
+          const int t = t_first + (n - co * a.up);
+          if (n >= a.N_total || t < 0 || t >= len_out) continue;
+          const long long yi = ybase + (long long)co * a.y_ld + t;
+          if (plain_out) {
+            const float val = (__uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f)) * a.out_alpha;
+            if (a.y_f16) reinterpret_cast<__half*>(a.y)[yi] = __float2half_rn(clamp_f16(val));
+            else reinterpret_cast<float*>(a.y)[yi] = val;
+          } else {
+            store_y(a, yi, finish(__uint_as_float(v[i]), a, co, rbase + (long long)co * a.r_ld + t, yi));
+          }
+        }
+      }
+    }
+  }
+}
+
+// SNAKE selects the staging family compiled into the kernel (anti-aliased SnakeBeta vs pointwise activations):
+// two smaller kernels allocate registers better than one with every path inlined.
+template <typename T, bool SNAKE>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int E = ElemTraits<T>::kEpc;
   constexpr bool kTf32 = ElemTraits<T>::kTf32;
@@ -277,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
       }
       for (int i = 0; i < a.acc_bufs; ++i) {
         mbar_init(acc_full + i, 1);
-        mbar_init(acc_empty + i, kEpiWarps);
+        mbar_init(acc_empty + i, kWorkerWarps - a.n_prod);
       }
       fence_mbar_init();
     }
@@ -296,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
   const int kc_per_panel = a.n_kchunks / a.n_panels;
   const int groups_per_panel = kc_per_panel * (a.KC / E);
 
-  if (warp < kProdWarps) {
+  if (warp < a.n_prod) {
     // ================================ producers ================================
     uint32_t ai = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -305,6 +621,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
       const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
       if (t0 >= len + extra_row || len <= 0) continue;
       const int t_lo = t0 - a.halo_l;
+      // pull this CTA's NEXT tile towards L2 while the current one is staged (the tile schedule is static)
+      if (a.l2_prefetch && a.n_panels == 1 && tile + (int)gridDim.x < a.total_tiles) {
+        const int ntile = tile + gridDim.x;
+        const int nb = ntile / a.tiles_per_utt;
+        const int nt0 = (ntile - nb * a.tiles_per_utt) * rows_tile;
+        const int nlen = a.len_in ? __ldg(a.len_in + nb) : a.L_in_max;
+        if (nt0 < nlen + extra_row && nlen > 0) {
+          const int esz = a.x_f16 ? 2 : 4, per_line = 128 / esz;
+          const int lo = max(nt0 - a.halo_l, 0) / per_line * per_line;
+          const int hi = min(nt0 - a.halo_l + a.R, nlen);
+          const int nlines = (hi - lo + per_line - 1) / per_line;
+          const char* base = reinterpret_cast<const char*>(a.x) + (long long)nb * a.x_bs * esz;
+          for (int idx = warp * 32 + lane; idx < a.Cin * nlines; idx += a.n_prod * 32) {
+            const int c = idx / nlines, l = idx - c * nlines;
+            prefetch_l2(base + ((long long)c * a.x_ld + lo + l * per_line) * esz);
+          }
+        }
+      }
       for (int nt = 0; nt < a.n_ntiles; ++nt) {
         if (!restage_per_nt && nt > 0) break;
         for (int pn = 0; pn < a.n_panels; ++pn, ++ai) {
@@ -312,21 +646,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
           mbar_wait(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
           T* smA = reinterpret_cast<T*>(smem + lay.a_off + buf * a.a_bytes);
           const int g0 = pn * groups_per_panel;
-          if (a.act == TB200_ACT_AA_SNAKEBETA) {
+          if constexpr (SNAKE) {
             // fast path: whole staged range (plus filter reach and load look-ahead) inside the utterance
             const bool interior = a.aa_fast && (t_lo - 16 >= 0) && (t_lo + a.R + 32 <= len);
             if (interior) {
               const int ncb = groups_per_panel * E / 32;
-              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, max(1, kProdWarps / ncb), smA, warp, lane);
+              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, (a.n_prod + ncb - 1) / ncb, smA, warp, lane);
             } else {
               const UmmaStore<T> st{smA, a.R};
-              stage_aa_snake<E, true>(a, b, t_lo, a.R, g0, groups_per_panel, len, st, scratch, warp, kProdWarps, lane);
+              stage_aa_snake<E, true>(a, b, t_lo, a.R, g0, groups_per_panel, len, st, scratch, warp, a.n_prod, lane);
             }
           } else {
+           if (a.pw_vec) {
+            if constexpr (E == 8) {
+              if (a.x_f16) stage_pointwise_vec<T, true>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
+              else stage_pointwise_vec<T, false>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
+            } else {
+              stage_pointwise_vec<T, false>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
+            }
+           } else {
             stage_pointwise_mlp<T>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
+           }
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"r"(a.n_prod * 32) : "memory");
           if (threadIdx.x == 0) mbar_arrive(a_full + buf);
         }
       }
@@ -423,9 +766,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
     }
   } else {
     // ================================ epilogue ================================
-    const int ew = warp - kEpiWarp0;
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half_id = ew >> 2;       // which half of the column slabs
+    const int n_epi = kWorkerWarps - a.n_prod;
+    const int ew = warp - a.n_prod;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int slab_step = n_epi >> 2;             // 1 or 2 warps per quarter split the 16-column slabs
+    const int slab0 = ew >> 2;
+    const int mode = a.epi_fast ? ((a.residual ? 1 : 0) + (a.accumulate ? 1 : 0)) : -1;
     uint32_t ac = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_utt;
@@ -436,69 +782,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
       const int len_out = a.up > 0 ? len * a.up : len;
       const int nsub = min(a.S, (rows - t0 + kTileM - 1) / kTileM);
       const long long ybase = (long long)b * a.y_bs, rbase = (long long)b * a.r_bs;
+      // pull the auxiliary rows (residual / old y) of this CTA's NEXT tile towards L2
+      if (a.l2_prefetch && mode >= 1 && a.n_ntiles == 1 && tile + (int)gridDim.x < a.total_tiles) {
+        const int ntile = tile + gridDim.x;
+        const int nb = ntile / a.tiles_per_utt;
+        const int nt0 = (ntile - nb * a.tiles_per_utt) * rows_tile;
+        const int nlen = a.len_in ? __ldg(a.len_in + nb) : a.L_in_max;
+        if (nt0 < nlen) {
+          const int esz = a.residual ? 4 : (a.y_f16 ? 2 : 4);
+          const char* base = a.residual ? reinterpret_cast<const char*>(a.residual) + (long long)nb * a.r_bs * 4
+                                        : reinterpret_cast<const char*>(a.y) + (long long)nb * a.y_bs * esz;
+          const int ld = a.residual ? a.r_ld : a.y_ld;
+          const int my_ch = ((a.NT / 16 - slab0 + slab_step - 1) / slab_step) * 16;   // channels this warp will drain
+          for (int idx = lane; idx < my_ch * a.S; idx += 32) {
+            const int ci = idx / a.S, sub = idx - ci * a.S;
+            const int ch = (slab0 + (ci >> 4) * slab_step) * 16 + (ci & 15);
+            const int row = nt0 + sub * kTileM + q * 32;
+            if (row < nlen) prefetch_l2(base + ((long long)ch * ld + row) * esz);
+          }
+        }
+      }
       for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
         const int abuf = ac % a.acc_bufs;
         mbar_wait(acc_full + abuf, (ac / a.acc_bufs) & 1);
         tc_fence_after();
         const int slabs = a.NT / 16;
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int m = t0 + sub * kTileM + q * 32 + lane;  // output row (regular) / input row (transposed)
-          for (int s = half_id; s < slabs; s += 2) {
-            uint32_t v[16];
-            __syncwarp();
-            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * a.S * a.NT + sub * a.NT + s * 16), v);
-            const int n0 = nt * a.NT + s * 16;
-            // every load is issued unconditionally (clamped addresses) before anything is consumed:
-            // the memory latency is paid once per slab, not once per column
-            if (a.up == 0) {
-              const bool row_ok = m < len_out;
-              const int tcl = min(m, len_out - 1);
-              float rres[16], racc[16];
-              if (a.residual) {
-                const float* rp = a.residual + rbase + tcl;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rres[i] = __ldg(rp + (long long)min(n0 + i, a.Cout - 1) * a.r_ld);
-              }
-              if (a.accumulate) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const long long yi = ybase + (long long)min(n0 + i, a.Cout - 1) * a.y_ld + tcl;
-                  racc[i] = a.y_f16 ? __half2float(reinterpret_cast<const __half*>(a.y)[yi]) : reinterpret_cast<const float*>(a.y)[yi];
-                }
-              }
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int co = min(n0 + i, a.Cout - 1);
-                float val = __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f);
-                if (a.out_act == TB200_OUT_TANH) val = tanhf(val);
-                else if (a.out_act == TB200_OUT_RELU) val = fmaxf(val, 0.f);
-                val *= a.out_alpha;
-                if (a.residual) val = fmaf(a.res_beta, rres[i], val);
-                if (a.accumulate) val += racc[i];
-                if (row_ok && n0 + i < a.N_total) store_y(a, ybase + (long long)co * a.y_ld + m, val);
-              }
-            } else {
-              // transposed conv: column n = co*u + phase lands at t = m*u + phase - u/2
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int n = n0 + i;
-                const int co = n / a.up;
-                const int t = m * a.up + (n - co * a.up) - a.up_pad;
-                if (n >= a.N_total || t < 0 || t >= len_out) continue;
-                float val = __uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f);
-                if (a.out_act == TB200_OUT_TANH) val = tanhf(val);
-                else if (a.out_act == TB200_OUT_RELU) val = fmaxf(val, 0.f);
-                val *= a.out_alpha;
-                const long long yi = ybase + (long long)co * a.y_ld + t;
-                if (a.residual) val = fmaf(a.res_beta, __ldg(a.residual + rbase + (long long)co * a.r_ld + t), val);
-                if (a.accumulate) val += a.y_f16 ? __half2float(reinterpret_cast<const __half*>(a.y)[yi]) : reinterpret_cast<const float*>(a.y)[yi];
-                store_y(a, yi, val);
-              }
-            }
-          }
-        }
+        const uint32_t tm0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * a.S * a.NT);
+        const int m_base = t0 + q * 32 + lane;
+        const EpiAux axr{a.residual, (uint32_t)rbase, (uint32_t)a.r_ld, 0, a.res_beta};
+        const EpiAux axy{a.y, (uint32_t)ybase, (uint32_t)a.y_ld, a.y_f16, 1.0f};
+        if (mode == 2) epilogue_plain<2>(a, axr, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        else if (mode == 1) epilogue_plain<1>(a, a.residual ? axr : axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        else if (mode == 0) epilogue_plain<0>(a, axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        else epilogue_generic(a, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, ybase, rbase);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + abuf);
@@ -528,9 +844,9 @@ static int device_props() {
 
 int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a);  // api.cu
 
-template <typename T>
+template <typename T, bool SNAKE>
 static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv1d_umma_kernel<T>;
+  auto kern = conv1d_umma_kernel<T, SNAKE>;
   static bool configured = false;
   if (!configured) {
     TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
@@ -548,12 +864,12 @@ static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
 static int plan(ConvArgs& a, int elem_bytes, int rows_max) {
   const int span = a.R - kTileM;  // halo rows (left + right)
   const int epc = 16 / elem_bytes;
-  const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kProdWarps * 2 * kAaScratch * 4 + 256;
+  const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kMaxProdWarps * 2 * kAaScratch * 4 + 256;
   const long long w_total = (long long)a.n_chunks * a.chunk_bytes;
   // pass 0 insists on weights resident in shared memory (no per-tile L2 re-streaming), pass 1 allows the ring
   for (int pass = 0; pass < 2; ++pass) {
     for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
-      for (int S = 4; S >= 1; S >>= 1) {
+      for (int S = TB200_MAX_S; S >= 1; S >>= 1) {
         if (S > 1 && ((S / 2) * kTileM >= rows_max)) continue;  // tile longer than the data
         if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < 2 * g_sm_count) continue;  // keep SMs busy
         if (S > 1 && 2 * S * a.NT > 512) continue;              // two accumulator buffers must fit in TMEM
@@ -602,10 +918,48 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   const int align = a.x_f16 ? 8 : 4;
   a.aa_fast = (a.act == TB200_ACT_AA_SNAKEBETA) && (a.Cin % 32 == 0) && ((a.Cin_pad / a.n_panels) % 32 == 0) &&
               (a.x_ld % align == 0) && (a.x_bs % align == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+  // vectorised pointwise staging: 16-byte loads along time
+  a.pw_vec = (a.act != TB200_ACT_AA_SNAKEBETA) && (a.x_ld % align == 0) && (a.x_bs % align == 0) &&
+             ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) && !(a.x_f16 && p->precision != TB200_PREC_F16) &&
+             !(a.act == TB200_ACT_LEAKY_RELU && (a.slope < 0.f || a.slope > 1.f));
+  // plain epilogue preconditions (see epilogue_plain)
+  {
+    const long long lim = 1LL << 31;
+    const long long y_ext = (long long)a.B * a.y_bs, r_ext = a.residual ? (long long)a.B * a.r_bs : 0;
+    a.epi_fast = a.up == 0 && a.out_act == TB200_OUT_NONE && a.N_total % 16 == 0 &&
+                 y_ext < lim && r_ext < lim && a.y_bs >= 0 && a.r_bs >= 0;
+  }
+  // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
+  // otherwise the epilogue is (6 + 8)
+  a.n_prod = (a.act == TB200_ACT_AA_SNAKEBETA) ? kMaxProdWarps : 6;
+  a.l2_prefetch = 0;  // measured: next-tile L2 prefetch doubles DRAM reads (lines evicted before use) -- kept as a knob
+  if (const char* e = getenv("TB200_L2_PREFETCH")) a.l2_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("TB200_MAX_S")) {  // tuning knob: cap the sub-tiles per CTA tile
+    const int cap = atoi(e);
+    if (cap >= 1 && a.S > cap) {
+      ConvArgs t = a;
+      // re-plan with a smaller S by shrinking rows_max-independent fields
+      const int span = a.R - a.S * kTileM;
+      t.S = cap; t.R = cap * kTileM + span;
+      t.a_bytes = a.a_bytes / a.R * t.R;
+      t.tiles_per_utt = (rows_max + cap * kTileM - 1) / (cap * kTileM);
+      t.total_tiles = t.tiles_per_utt * a.B;
+      int cols = 32;
+      while (cols < t.acc_bufs * cap * a.NT) cols <<= 1;
+      t.tmem_cols = cols;
+      a = t;
+    }
+  }
+  if (const char* e = getenv(a.act == TB200_ACT_AA_SNAKEBETA ? "TB200_NPROD_SNAKE" : "TB200_NPROD_PW")) {  // tuning knob
+    const int v = atoi(e);
+    if (v == 6 || v == 10) a.n_prod = v;
+  }
   const int smem_bytes = ws_layout(a).total;
   if (smem_bytes > g_max_smem) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
-  if (p->precision == TB200_PREC_F16) return launch_t<__half>(a, smem_bytes, stream);
-  return launch_t<float>(a, smem_bytes, stream);
+  const bool snake = a.act == TB200_ACT_AA_SNAKEBETA;
+  if (p->precision == TB200_PREC_F16)
+    return snake ? launch_t<__half, true>(a, smem_bytes, stream) : launch_t<__half, false>(a, smem_bytes, stream);
+  return snake ? launch_t<float, true>(a, smem_bytes, stream) : launch_t<float, false>(a, smem_bytes, stream);
 }
 
 }  // namespace tb200

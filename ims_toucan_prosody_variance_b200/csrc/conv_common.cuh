@@ -46,6 +46,10 @@ struct ConvArgs {
   int a_bufs, acc_bufs;   // staged-input / accumulator buffers (pipeline depth)
   int n_panels;           // input-channel panels staged one at a time (1 = all channels at once)
   int aa_fast;            // lane=channel snake staging allowed (alignment / channel-count preconditions)
+  int pw_vec;             // vectorised pointwise staging allowed (alignment preconditions)
+  int epi_fast;           // plain epilogue allowed (see epilogue_plain)
+  int l2_prefetch;        // next-tile L2 prefetch (tuning knob, off by default)
+  int n_prod;             // producer warps (the other worker warps run the epilogue)
 };
 
 struct ConvGeom {
