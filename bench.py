@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
 
-Workload (BASELINE.json configs[1]): BigVGAN generator alone, batch 64 synthetic 80-bin mel
-spectrograms x 500 frames -> 24 kHz wave (512 s of audio per step per GPU).  One process per GPU;
-under torchrun every rank synthesises its own shard of 64 utterances (weak scaling, no collective on
-the data path; NCCL only gathers output lengths and the max-over-ranks time).
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): BigVGAN generator
+alone, batch 64 synthetic 80-bin mel spectrograms x 500 frames -> 24 kHz wave (512 s of audio per step per
+GPU).  `--workload acoustic` is configs[2] (ToucanTTS, 128 ragged phoneme sequences <= 200 tokens -> mel) and
+`--workload e2e` the per-GPU shard of configs[3] (64 utterances text -> wave); both are extra measurements,
+not the headline.  One process per GPU; under torchrun every rank synthesises its own shard (weak scaling, no
+collective on the data path; NCCL only gathers output lengths and the max-over-ranks time).
 
 Prints ONE JSON line (see the contract in the task description): `value` is device-timed with the
 mels resident in HBM, `e2e` goes through the module's public batched call with pinned HOST buffers
@@ -163,6 +165,148 @@ def workload_config(args):
             "l2": "working set per step (>6 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
+def tts_flops(t_list, f_list, with_vocoder):
+    """Algorithmic FLOPs of the acoustic model: 24.5 M per phoneme + 63.8 M per frame +
+    9 216 (T^2 + F^2) attention; plus 648.24 M per frame for the vocoder."""
+    fl = 0.0
+    for t, f in zip(t_list, f_list):
+        fl += 24.5e6 * t + 63.8e6 * f + 9216.0 * (t * t + f * f)
+        if with_vocoder:
+            fl += FLOP_PER_FRAME * (2 * (f // 2))
+    return fl
+
+
+def run_tts_workload(args, rank, local_rank, world, dev, dist):
+    """configs[2] (acoustic: 128 ragged utterances -> mel) and the per-GPU shard of configs[3] (e2e: 64 utterances
+    text -> wave through BigVGAN/HiFiGAN).  Same JSON contract as the vocoder workload."""
+    import random
+
+    import ims_toucan_prosody_variance_b200 as tb
+    from ims_toucan_prosody_variance_b200 import ops
+    from oracle import factory, restate
+    e2e_mode = args.workload == "e2e"
+    n_utt = args.batch if args.batch_given else (64 if e2e_mode else 128)
+    tsd = factory.make_state_dict("toucantts", 1234)
+    tts = tb.ToucanTTS(weights=tsd, precision=args.acoustic_precision).to(dev)
+    tts.store_inverse_all()
+    voc = vsd = None
+    if e2e_mode:
+        voc, vsd = build_generator(args.vocoder, args.precision, dev)
+    rng = random.Random(3 + rank)
+    lens = [rng.randint(20, 200) for _ in range(n_utt)]
+    t_max = max(lens)
+    text_host = torch.zeros((n_utt, t_max, 62), dtype=torch.float32)
+    for i, n in enumerate(lens):
+        text_host[i, :n] = factory.make_phoneme_tensor(n, 1000 * rank + i)
+    text_host = text_host.pin_memory()
+    emb = torch.stack([factory.make_utterance_embedding(i) for i in range(n_utt)]).to(dev)
+    tlen = torch.tensor(lens, dtype=torch.int32)
+    lang = torch.full((n_utt,), 12, dtype=torch.int64)
+    text_dev = text_host.to(dev)
+    eng = tb.TextToWave(tts, voc) if e2e_mode else None
+
+    def step(text):
+        if e2e_mode:
+            wave, wlen, r = eng.synthesize_padded(text, tlen, emb, lang_ids=lang, noise="device")
+            return wave, wlen, r
+        r = tts.synthesize_batch(text, tlen, utterance_embedding=emb, lang_ids=lang, noise="device")
+        return r["mel_ncl"], r["mel_lengths"], r
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        out, out_len, r = step(text_dev)
+    barrier()
+    frames = [int(v) for v in r["frames_host"]]
+    audio_s = sum(2 * (f // 2) for f in frames) * SAMPLES_PER_FRAME / SAMPLE_RATE
+    launches0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out, out_len, r = step(text_dev)
+    ev1.record()
+    barrier()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (ops.LAUNCHES - launches0) // args.steps
+    out_host = torch.empty(out.shape, dtype=torch.float32).pin_memory()   # durations are noise-independent: fixed shape
+
+    def e2e_step():
+        t = text_host.to(dev, non_blocking=True)
+        o, _, _ = step(t)
+        out_host.copy_(o, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    # the only collective: output lengths + whole-job audio seconds
+    from ims_toucan_prosody_variance_b200 import sharding
+    all_len = sharding.gather_output_lengths(range(rank * n_utt, (rank + 1) * n_utt), out_len.to(torch.int64), world * n_utt, device=dev)
+    total_audio, _ = sharding.reduce_metrics(audio_s, ms_step, device=dev)
+    assert int(all_len.sum()) > 0 and bool(torch.isfinite(out[0, ..., :int(out_len[0])]).all())
+    if rank != 0:
+        return
+    value = total_audio / (ms_step / 1e3)
+    tflops_peak, hbm_peak, peak_src = peaks()
+    flops = tts_flops(lens, frames, e2e_mode)
+    achieved = flops / (ms_step / 1e3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        tf = restate.fold_weight_norm(tsd)
+        vf = restate.fold_weight_norm(vsd) if e2e_mode else None
+        text1 = factory.make_phoneme_tensor(100, 1)
+        best, fr = float("inf"), 0
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with torch.inference_mode():
+                ref = restate.toucantts_forward(tf, text1, factory.make_utterance_embedding(1), lang_id=12)
+                if e2e_mode:
+                    (restate.bigvgan_forward if args.vocoder == "bigvgan" else restate.hifigan_forward)(vf, ref["mel"].t())
+            best = min(best, time.perf_counter() - t0)
+            fr = ref["mel"].shape[0]
+        cpu = {"value": round(fr * SAMPLES_PER_FRAME / SAMPLE_RATE / best, 3), "unit": UNIT, "cores": os.cpu_count() or 1,
+               "kind": "port", "sample": f"1 utterance x 100 phonemes ({fr} frames), batch-1, best of 2"}
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.acoustic_precision, "data": "synthetic",
+        "config": {"workload": (f"text->wave, {n_utt} ragged utterances (20..200 phonemes) per GPU through ToucanTTS + {args.vocoder}"
+                                if e2e_mode else f"ToucanTTS acoustic model only: {n_utt} ragged phoneme sequences (20..200 tokens) -> mel, per GPU"),
+                   "utterances_per_gpu": n_utt, "phonemes": sum(lens), "frames": sum(frames), "acoustic_precision": args.acoustic_precision,
+                   "vocoder": args.vocoder if e2e_mode else None, "weights": "random-init (oracle.factory seed 1234, calibrated duration head)",
+                   "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": round(total_audio / (ms_e2e / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": text_host.numel() * 4,
+                "d2h_bytes_per_step": out.numel() * 4, "ms_per_step": round(ms_e2e, 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": tflops_peak, "unit": "TFLOP/s",
+                     "frac": round(achieved / tflops_peak, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": "whole step (conv1d_umma + acoustic kernels); algorithmic FLOPs per SURVEY.md 8d"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,10 +315,15 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--vocoder", default="bigvgan", choices=["bigvgan", "hifigan"])
     ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "acoustic", "e2e"])
+    ap.add_argument("--acoustic-precision", default="tf32", choices=["tf32", "f16", "fp32"])
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--frames", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = 64
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
 
     if args.impl == "reference":
@@ -193,6 +342,12 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload != "vocoder":
+        run_tts_workload(args, rank, local_rank, world, dev, dist)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     from ims_toucan_prosody_variance_b200 import ops
     from oracle import factory
@@ -274,10 +429,17 @@ def main():
     tflops_peak, hbm_peak, peak_src = peaks()
     flops_step = FLOP_PER_FRAME * args.batch * args.frames
     achieved = flops_step / (ms_step / 1e3) / 1e12  # per GPU: each rank does the same work in ms_step
+    traffic = None   # DRAM bytes per launch of the same kernel, from the committed ncu pass (profiles/)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{args.vocoder}_b{args.batch}_f{args.frames}_{args.precision}")
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": tflops_peak, "unit": "TFLOP/s",
-                "frac": round(achieved / tflops_peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": "conv1d_umma_kernel (all conv launches of one step; algorithmic FLOPs = "
-                          f"{FLOP_PER_FRAME} per mel frame x {args.batch * args.frames} frames)"}
+                "frac": round(achieved / tflops_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "kernel": "conv1d_umma_kernel: the step is its launches back to back, so achieved = (algorithmic FLOPs per "
+                          f"launch = {FLOP_PER_FRAME} per mel frame x {args.batch * args.frames} frames / {int(launches)} launches) / "
+                          "(average launch duration = CUDA-event step time / launches)",
+                "launch_ms_avg": round(ms_step / max(int(launches), 1), 4)}
 
     cpu = None
     if not args.no_cpu_baseline:
