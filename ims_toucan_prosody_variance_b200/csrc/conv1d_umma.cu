@@ -35,6 +35,9 @@
 #ifndef TB200_ROLE_INLINE
 #define TB200_ROLE_INLINE __forceinline__
 #endif
+#ifndef TB200_LDMODE
+#define TB200_LDMODE 0   // 0: ld.global.nc (LDG.E.CONSTANT)   1: ld.global.cg (L2 only, no L1 allocation)
+#endif
 #ifndef TB200_MAX_S
 #define TB200_MAX_S 8
 #endif
@@ -194,8 +197,9 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
       const int c = g0 * E + gs * CH + e;
       if (ok && c < a.Cin) {
         const long long idx = xb + (long long)c * a.x_ld + tq;
-        v[e] = XF16 ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + idx))
-                    : __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.x) + idx));
+        const uint4* src = XF16 ? reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.x) + idx)
+                                : reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.x) + idx);
+        v[e] = TB200_LDMODE ? __ldcg(src) : __ldg(src);
       } else {
         v[e] = make_uint4(0u, 0u, 0u, 0u);
       }
@@ -455,11 +459,11 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux
     if (ax.f16) {
       const __half* p = reinterpret_cast<const __half*>(ax.ptr);
 #pragma unroll
-      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = __half2float(p[off]);
+      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = __half2float(TB200_LDMODE ? __ldcg(p + off) : p[off]);
     } else {
       const float* p = reinterpret_cast<const float*>(ax.ptr);
 #pragma unroll
-      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = p[off];
+      for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = TB200_LDMODE ? __ldcg(p + off) : p[off];
     }
   };
   float bias[16];   // bias * out_alpha
@@ -561,8 +565,10 @@ __device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t t
 
 // SNAKE selects the staging family compiled into the kernel (anti-aliased SnakeBeta vs pointwise activations):
 // two smaller kernels allocate registers better than one with every path inlined.
-template <typename T, bool SNAKE>
-__global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
+// CTAS = resident CTAs per SM: 2 halves the per-CTA registers (64), shared memory and TMEM columns but doubles the
+// independent warps (and scoreboards) that hide global-memory latency -- used for the pointwise staging family.
+template <typename T, bool SNAKE, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int E = ElemTraits<T>::kEpc;
   constexpr bool kTf32 = ElemTraits<T>::kTf32;
   constexpr int kStepK = 2 * E;  // K per tcgen05.mma
@@ -651,7 +657,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_umma_kernel(const __grid_c
             const bool interior = a.aa_fast && (t_lo - 16 >= 0) && (t_lo + a.R + 32 <= len);
             if (interior) {
               const int ncb = groups_per_panel * E / 32;
-              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, (a.n_prod + ncb - 1) / ncb, smA, warp, lane);
+              // row segments per 32-channel block: tasks = ncb * nseg is a multiple of the producer warps (balanced rounds)
+              int gcd = ncb, r2 = a.n_prod;
+              while (r2) {
+                const int tmp = gcd % r2;
+                gcd = r2;
+                r2 = tmp;
+              }
+              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, a.n_prod / gcd, smA, warp, lane);
             } else {
               const UmmaStore<T> st{smA, a.R};
               stage_aa_snake<E, true>(a, b, t_lo, a.R, g0, groups_per_panel, len, st, scratch, warp, a.n_prod, lane);
@@ -844,15 +857,16 @@ static int device_props() {
 
 int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a);  // api.cu
 
-template <typename T, bool SNAKE>
+template <typename T, bool SNAKE, int CTAS>
 static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
-  auto kern = conv1d_umma_kernel<T, SNAKE>;
+  auto kern = conv1d_umma_kernel<T, SNAKE, CTAS>;
   static bool configured = false;
   if (!configured) {
-    TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem / CTAS));
     configured = true;
   }
-  int grid = g_sm_count < a.total_tiles ? g_sm_count : a.total_tiles;  // persistent: one CTA per SM
+  const int slots = g_sm_count * CTAS;
+  int grid = slots < a.total_tiles ? slots : a.total_tiles;  // persistent: CTAS CTAs per SM
   if (grid < 1) grid = 1;
   kern<<<grid, kThreads, smem_bytes, stream>>>(a);
   TB200_CUDA_CHECK(cudaGetLastError());
@@ -861,7 +875,9 @@ static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
 
 // Choose sub-tiles per CTA tile (S), buffer counts and the channel-panel split so that everything fits
 // in shared memory / the 512 TMEM columns.
-static int plan(ConvArgs& a, int elem_bytes, int rows_max) {
+static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas) {
+  const int smem_cap = ctas == 1 ? g_max_smem : (g_max_smem + 1024) / ctas - 1024 - 512;  // 1 KB reserved per resident CTA
+  const int tmem_cap = 512 / ctas;
   const int span = a.R - kTileM;  // halo rows (left + right)
   const int epc = 16 / elem_bytes;
   const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kMaxProdWarps * 2 * kAaScratch * 4 + 256;
@@ -871,14 +887,15 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max) {
     for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
       for (int S = TB200_MAX_S; S >= 1; S >>= 1) {
         if (S > 1 && ((S / 2) * kTileM >= rows_max)) continue;  // tile longer than the data
-        if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < 2 * g_sm_count) continue;  // keep SMs busy
-        if (S > 1 && 2 * S * a.NT > 512) continue;              // two accumulator buffers must fit in TMEM
-        const int acc_bufs = 2 * S * a.NT <= 512 ? 2 : 1;
+        if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < 2 * g_sm_count * ctas) continue;  // keep SMs busy
+        if (S > 1 && 2 * S * a.NT > tmem_cap) continue;         // two accumulator buffers must fit in TMEM
+        if (S * a.NT > tmem_cap) continue;
+        const int acc_bufs = 2 * S * a.NT <= tmem_cap ? 2 : 1;
         const int R = S * kTileM + span;
         for (int n_panels = 1; n_panels <= a.n_kchunks; ++n_panels) {
           if (a.n_kchunks % n_panels) continue;
           const int a_bytes = (a.Cin_pad / n_panels / epc) * R * 16;
-          const long long budget = (long long)g_max_smem - fixed - (long long)a_bufs * a_bytes;
+          const long long budget = (long long)smem_cap - fixed - (long long)a_bufs * a_bytes;
           if (budget < 2LL * a.chunk_bytes) continue;
           const bool resident = w_total <= budget && a.n_chunks <= kMaxRing;
           if (pass == 0 && (!resident || n_panels > 1)) continue;
@@ -912,8 +929,25 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   if (rc) return rc;
   const int elem_bytes = p->precision == TB200_PREC_F16 ? 2 : 4;
   const int rows_max = p->L_in_max + (a.up > 0 ? 1 : 0);
-  rc = plan(a, elem_bytes, rows_max);
-  if (rc) return rc;
+  // pointwise staging family: try two resident CTAs per SM first (more independent warps in flight); only when
+  // the weights stay resident in the smaller shared-memory share, else one CTA per SM
+  const bool snake = a.act == TB200_ACT_AA_SNAKEBETA;
+  int ctas = 1;
+  {
+    int want = 1;   // two CTAs per SM measured slower (the 64-register cap spills); kept as a knob
+    if (const char* e = getenv("TB200_CTAS")) want = atoi(e) == 2 ? 2 : 1;   // tuning knob
+    if (want == 2) {
+      ConvArgs t = a;
+      if (plan(t, elem_bytes, rows_max, 2) == 0 && t.resident && t.n_panels == 1) {
+        a = t;
+        ctas = 2;
+      }
+    }
+  }
+  if (ctas == 1) {
+    rc = plan(a, elem_bytes, rows_max, 1);
+    if (rc) return rc;
+  }
   // lane=channel snake staging: 16-byte loads need an aligned base / pitch and 32-channel blocks
   const int align = a.x_f16 ? 8 : 4;
   a.aa_fast = (a.act == TB200_ACT_AA_SNAKEBETA) && (a.Cin % 32 == 0) && ((a.Cin_pad / a.n_panels) % 32 == 0) &&
@@ -955,11 +989,13 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
     if (v == 6 || v == 10) a.n_prod = v;
   }
   const int smem_bytes = ws_layout(a).total;
-  if (smem_bytes > g_max_smem) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
-  const bool snake = a.act == TB200_ACT_AA_SNAKEBETA;
-  if (p->precision == TB200_PREC_F16)
-    return snake ? launch_t<__half, true>(a, smem_bytes, stream) : launch_t<__half, false>(a, smem_bytes, stream);
-  return snake ? launch_t<float, true>(a, smem_bytes, stream) : launch_t<float, false>(a, smem_bytes, stream);
+  if (smem_bytes > g_max_smem / ctas) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
+  if (p->precision == TB200_PREC_F16) {
+    if (snake) return launch_t<__half, true, 1>(a, smem_bytes, stream);
+    return ctas == 2 ? launch_t<__half, false, 2>(a, smem_bytes, stream) : launch_t<__half, false, 1>(a, smem_bytes, stream);
+  }
+  if (snake) return launch_t<float, true, 1>(a, smem_bytes, stream);
+  return ctas == 2 ? launch_t<float, false, 2>(a, smem_bytes, stream) : launch_t<float, false, 1>(a, smem_bytes, stream);
 }
 
 }  // namespace tb200
