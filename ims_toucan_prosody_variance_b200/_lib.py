@@ -44,6 +44,7 @@ SIGNATURES = {
     "tb200_length_regulate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "tb200_debug_trace_read": (c_int, [c_void_p, c_int]),
     "tb200_channel_norm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "tb200_group_norm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,

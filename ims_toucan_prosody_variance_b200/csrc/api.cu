@@ -146,6 +146,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream);
+int conv_trace_read(long long* host_out, int n);
 int conv1d_simt(const tb200_conv1d_params* p, cudaStream_t stream);
 
 }  // namespace tb200
@@ -187,6 +188,11 @@ int tb200_pack_conv_weight(const float* w, void* w_packed, int32_t C_in, int32_t
     pack_weight_kernel<float><<<blocks, 256, 0, s>>>(w, reinterpret_cast<float*>(w_packed), C_in, C_out, K, up, g);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+int tb200_debug_trace_read(int64_t* host_out, int32_t n) {
+  if (!host_out || n <= 0) return fail(TB200_E_BADARG, "trace: bad argument");
+  return conv_trace_read(reinterpret_cast<long long*>(host_out), n);
 }
 
 int tb200_conv1d(const tb200_conv1d_params* p, void* stream) {

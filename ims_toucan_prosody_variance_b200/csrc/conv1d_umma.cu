@@ -64,6 +64,14 @@ struct ElemTraits<float> {
   static constexpr bool kTf32 = true;
 };
 
+// Optional per-tile timeline of CTA 0 (TB200_TRACE=1, debugging aid): clock64() stamps per tile.
+//  0 producer: a_empty acquired   1 producer: tile staged     2 MMA: a_full acquired   3 MMA: all MMAs issued
+//  4 epilogue: acc_full acquired  5 epilogue: tile drained    6 MMA: acc_empty acquired
+constexpr int kTraceTiles = 96;
+__device__ __forceinline__ void trace(const ConvArgs& a, int slot, uint32_t idx) {
+  if (a.trace && blockIdx.x == 0 && idx < (uint32_t)kTraceTiles) a.trace[idx * 8 + slot] = clock64();
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -187,7 +195,7 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
   const long long xb = (long long)b * a.x_bs;
   const bool simple_act = a.act == TB200_ACT_NONE || a.act == TB200_ACT_LEAKY_RELU || a.act == TB200_ACT_RELU;
   const __half2 slope2 = __float2half2_rn(a.slope);
-  uint4 bufa[CH], bufb[CH], bufc[CH];
+  uint4 bufa[CH], bufb[CH];
   auto issue = [&](int task, uint4 (&v)[CH]) {
     const int gs = task / nqb, q = (task - gs * nqb) * 32 + lane;
     const int tq = t_al + V * q;
@@ -287,23 +295,16 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
       }
     }
   };
-  // three register sets rotate between "in flight" (two tasks ahead) and "being converted": no copies at the loop edge
-  int task = pw;
+  // Batches of 2 tasks: the 2 x CH 16-byte loads of a batch are issued back to back, then both tasks are converted.
+  // (A rotating scheme with one task of look-ahead pays one full memory latency per task -- the per-tile trace
+  // showed 3.4 K cycles per task; a batch pays it once per 2 tasks with the same register footprint.  Larger
+  // batches spill, and with the L1 carved out for shared memory a spill costs a DRAM round trip.)
   const int P = kProdWarps;
-  if (task < ntask) issue(task, bufa);
-  if (task + P < ntask) issue(task + P, bufb);
-  while (task < ntask) {
-    if (task + 2 * P < ntask) issue(task + 2 * P, bufc);
-    process(task, bufa);
-    task += P;
-    if (task >= ntask) break;
-    if (task + 2 * P < ntask) issue(task + 2 * P, bufa);
-    process(task, bufb);
-    task += P;
-    if (task >= ntask) break;
-    if (task + 2 * P < ntask) issue(task + 2 * P, bufb);
-    process(task, bufc);
-    task += P;
+  for (int task0 = pw; task0 < ntask; task0 += 2 * P) {
+    issue(task0, bufa);
+    if (task0 + P < ntask) issue(task0 + P, bufb);
+    process(task0, bufa);
+    if (task0 + P < ntask) process(task0 + P, bufb);
   }
 }
 
@@ -495,16 +496,13 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux
   };
   float ra[16], rb[16];
   if constexpr (NAUX == 1) {
-    // two register sets: the rows of item k+1 are in flight while item k is finished
-    int k = 0;
-    if (k < nitems) fetch1(k, ax0, ra);
-    while (k < nitems) {
+    // batches of 2 items: 32 row loads requested back to back, then both items drained (one memory latency per
+    // 2 items; one item of look-ahead pays it per item -- measured 3.3 K cycles per 16-column item)
+    for (int k = 0; k < nitems; k += 2) {
+      fetch1(k, ax0, ra);
       if (k + 1 < nitems) fetch1(k + 1, ax0, rb);
       finish_item(k, ra, ra);
-      if (++k >= nitems) break;
-      if (k + 1 < nitems) fetch1(k + 1, ax0, ra);
-      finish_item(k, rb, rb);
-      ++k;
+      if (k + 1 < nitems) finish_item(k + 1, rb, rb);
     }
   } else if constexpr (NAUX == 2) {
     // two inputs (rare: last pair of the 2nd/3rd residual block of a stage): 32 loads per item, no look-ahead
@@ -650,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
         for (int pn = 0; pn < a.n_panels; ++pn, ++ai) {
           const int buf = ai % a.a_bufs;
           mbar_wait(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
+          if (threadIdx.x == 0) trace(a, 0, ai);
           T* smA = reinterpret_cast<T*>(smem + lay.a_off + buf * a.a_bytes);
           const int g0 = pn * groups_per_panel;
           if constexpr (SNAKE) {
@@ -683,7 +682,10 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, %0;" ::"r"(a.n_prod * 32) : "memory");
-          if (threadIdx.x == 0) mbar_arrive(a_full + buf);
+          if (threadIdx.x == 0) {
+            trace(a, 1, ai);
+            mbar_arrive(a_full + buf);
+          }
         }
       }
     }
@@ -736,11 +738,13 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
         for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
           const int abuf = ac % a.acc_bufs;
           mbar_wait(acc_empty + abuf, ((ac / a.acc_bufs) & 1) ^ 1);
+          trace(a, 6, ac);
           const uint32_t acc_col = tmem_base + (uint32_t)(abuf * a.S * a.NT);
           for (int pn = 0; pn < a.n_panels; ++pn) {
             if (restage_per_nt || nt == 0) {
               a_buf_cur = ai % a.a_bufs;
               mbar_wait(a_full + a_buf_cur, (ai / a.a_bufs) & 1);
+              trace(a, 2, ai);
               ++ai;
             }
             tc_fence_after();
@@ -773,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
             if (restage_per_nt || nt == a.n_ntiles - 1) umma_commit(a_empty + a_buf_cur);
           }
           umma_commit(acc_full + abuf);
+          trace(a, 3, ac);
         }
         first_tile = false;
       }
@@ -818,6 +823,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
       for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
         const int abuf = ac % a.acc_bufs;
         mbar_wait(acc_full + abuf, (ac / a.acc_bufs) & 1);
+        if (ew == 0 && lane == 0) trace(a, 4, ac);
         tc_fence_after();
         const int slabs = a.NT / 16;
         const uint32_t tm0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * a.S * a.NT);
@@ -830,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
         else epilogue_generic(a, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, ybase, rbase);
         tc_fence_before();
         __syncwarp();
+        if (ew == 0 && lane == 0) trace(a, 5, ac);
         if (lane == 0) mbar_arrive(acc_empty + abuf);
       }
     }
@@ -843,6 +850,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
+static long long* g_trace = nullptr;   // TB200_TRACE=1 only (debugging aid; the one allocation the library ever makes)
 static int g_sm_count = 0;
 static int g_max_smem = 0;
 
@@ -966,6 +974,12 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
   // otherwise the epilogue is (6 + 8)
   a.n_prod = (a.act == TB200_ACT_AA_SNAKEBETA) ? kMaxProdWarps : 6;
+  a.trace = nullptr;
+  if (getenv("TB200_TRACE")) {
+    if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceTiles * 8 * sizeof(long long)));
+    TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, kTraceTiles * 8 * sizeof(long long), stream));
+    a.trace = g_trace;
+  }
   a.l2_prefetch = 0;  // measured: next-tile L2 prefetch doubles DRAM reads (lines evicted before use) -- kept as a knob
   if (const char* e = getenv("TB200_L2_PREFETCH")) a.l2_prefetch = atoi(e) != 0;
   if (const char* e = getenv("TB200_MAX_S")) {  // tuning knob: cap the sub-tiles per CTA tile
@@ -996,6 +1010,12 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   }
   if (snake) return launch_t<float, true, 1>(a, smem_bytes, stream);
   return ctas == 2 ? launch_t<float, false, 2>(a, smem_bytes, stream) : launch_t<float, false, 1>(a, smem_bytes, stream);
+}
+
+int conv_trace_read(long long* host_out, int n) {
+  if (!g_trace) return fail(TB200_E_BADARG, "trace: TB200_TRACE was not set");
+  TB200_CUDA_CHECK(cudaMemcpy(host_out, g_trace, sizeof(long long) * (n < kTraceTiles * 8 ? n : kTraceTiles * 8), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 }  // namespace tb200

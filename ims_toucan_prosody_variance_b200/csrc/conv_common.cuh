@@ -49,6 +49,7 @@ struct ConvArgs {
   int pw_vec;             // vectorised pointwise staging allowed (alignment preconditions)
   int epi_fast;           // plain epilogue allowed (see epilogue_plain)
   int l2_prefetch;        // next-tile L2 prefetch (tuning knob, off by default)
+  long long* trace;       // per-tile clock64() stamps of CTA 0 (TB200_TRACE debugging aid) or nullptr
   int n_prod;             // producer warps (the other worker warps run the epilogue)
 };
 

@@ -170,6 +170,11 @@ int tb200_length_regulate(const float* enc, int64_t enc_bs, int32_t enc_ld,
                           float* out, int64_t out_bs, int32_t out_ld,
                           int32_t* frame_to_phone, int32_t f2p_ld, void* stream);
 
+/* Debugging aid (not part of the reference-facing surface): with the environment variable TB200_TRACE set,
+ * tb200_conv1d records clock64() stamps of its pipeline roles for the first tiles of CTA 0; this copies up to
+ * n int64 values (8 per tile) to host memory after a device synchronisation by the caller.               */
+int tb200_debug_trace_read(int64_t* host_out, int32_t n);
+
 /* ------------------------------------------------------------------------------------------
  * Acoustic model (ToucanTTS) -- the non-GEMM kernels.  All fp32, NCL tensors, ragged by `len`
  * (device int32 (B) or NULL = L_max): positions >= len[b] are neither read as data nor written.

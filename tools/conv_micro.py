@@ -35,3 +35,16 @@ ms = e0.elapsed_time(e1) / reps
 flops = 2.0 * B * L * cin * cout * (up or 1) * (2 if up else k)
 byts = B * L * (cin * 4 + cout * (up or 1) * 8)
 print(f"Cin={cin} Cout={cout} K={k} dil={dil} up={up} L={L} B={B} act={act} {prec}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
+
+if os.environ.get("TB200_TRACE"):
+    import ctypes
+
+    from ims_toucan_prosody_variance_b200 import _lib
+    buf = (ctypes.c_int64 * (96 * 8))()
+    _lib.check(_lib.load().tb200_debug_trace_read(ctypes.cast(buf, ctypes.c_void_p), 96 * 8), "trace")
+    t = torch.tensor(list(buf), dtype=torch.int64).reshape(96, 8)
+    base = int(t[:, :7][t[:, :7] > 0].min())
+    print("tile  a_empty  staged | a_full  mma_issued  acc_empty(mma) | acc_full  drained   (clock cycles since first stamp)")
+    for i in range(24):
+        r = [int(v) - base if int(v) > 0 else -1 for v in t[i, :7]]
+        print(f"{i:4d} {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[6]:8d} | {r[4]:8d} {r[5]:8d}   stage {r[1]-r[0]:6d}  mma-issue {r[3]-r[2]:6d}  mma->accfull {r[4]-r[3]:6d}  drain {r[5]-r[4]:6d}")

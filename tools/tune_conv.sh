@@ -1,12 +1,8 @@
 #!/bin/bash
 out=gpurun_out/${1:-tune}.log
 : > $out
-P=$PWD/ims_toucan_prosody_variance_b200
-run() {
-  python tools/conv_micro.py 32 32 3 1 0 192000 64 1 f16 3 >> $out 2>&1
-  python tools/conv_micro.py 64 64 11 1 0 96000 64 1 f16 3 >> $out 2>&1
-  python tools/conv_micro.py 64 64 11 1 0 96000 64 2 f16 3 >> $out 2>&1
-  python tools/conv_micro.py 128 128 3 1 0 24000 64 1 f16 3 >> $out 2>&1
-}
-echo "== ldg.nc" >> $out; run
-echo "== ld.cg" >> $out; TB200_LIB=$P/libtb_cg.so run
+python tools/conv_micro.py 32 32 3 1 0 192000 64 1 f16 3 >> $out 2>&1
+python tools/conv_micro.py 64 64 11 1 0 96000 64 1 f16 3 >> $out 2>&1
+python tools/conv_micro.py 64 64 11 1 0 96000 64 2 f16 3 >> $out 2>&1
+python tools/conv_micro.py 32 32 3 1 0 192000 64 2 f16 3 >> $out 2>&1
+python tools/conv_micro.py 128 128 3 1 0 24000 64 1 f16 3 >> $out 2>&1
