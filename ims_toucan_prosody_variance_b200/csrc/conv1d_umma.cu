@@ -44,11 +44,25 @@
 
 namespace tb200 {
 
-constexpr int kWorkerWarps = 14;           // producers [0, a.n_prod) + epilogue [a.n_prod, 14): split chosen per launch
-constexpr int kMmaWarp = kWorkerWarps;
-constexpr int kLoadWarp = kWorkerWarps + 1;
-constexpr int kThreads = (kWorkerWarps + 2) * 32;  // 512: 4 warps per SM sub-partition -> 128 registers per thread
-constexpr int kMaxProdWarps = 10;
+// Worker warps = producers [0, a.n_prod) + epilogue [a.n_prod, W); warp W issues the MMAs, warp W+1 loads weights.
+//   pointwise staging family: W = 14 (16 warps, 128 registers per thread)
+//   snake staging family:     W = 22 (24 warps,  80 registers per thread): the anti-aliased snake is a chain of
+//   dependent FMAs (one instruction per ~4.5 cycles per warp), so it wants warps, not registers.
+#ifndef TB200_SNAKE_EPI_BATCH
+#define TB200_SNAKE_EPI_BATCH 1
+#endif
+#ifndef TB200_SNAKE_WORKERS
+#define TB200_SNAKE_WORKERS 22
+#endif
+template <bool SNAKE>
+struct Roles {
+  static constexpr int kWorkers = SNAKE ? TB200_SNAKE_WORKERS : 14;
+  static constexpr int kMma = kWorkers;
+  static constexpr int kLoad = kWorkers + 1;
+  static constexpr int kThreads = (kWorkers + 2) * 32;
+};
+constexpr int kMaxProdWarps = 18;
+constexpr int kBiasCache = 512;             // floats of (bias * out_alpha) cached in shared memory for the plain epilogue
 constexpr int kMaxRing = 64;
 
 template <typename T>
@@ -411,7 +425,7 @@ __device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int
 // the kernel
 // ---------------------------------------------------------------------------------------------
 struct WsLayout {  // shared-memory carve-up, computed identically on host and device
-  int a_off, w_off, bar_off, tmem_off, scratch_off, total;
+  int a_off, w_off, bar_off, tmem_off, scratch_off, bias_off, total;
 };
 __host__ __device__ inline WsLayout ws_layout(const ConvArgs& a) {
   WsLayout l;
@@ -421,7 +435,8 @@ __host__ __device__ inline WsLayout ws_layout(const ConvArgs& a) {
   const int nbars = 2 * a.ring_slots + 2 * a.a_bufs + 2 * a.acc_bufs;
   l.tmem_off = l.bar_off + nbars * 8;
   l.scratch_off = l.tmem_off + 16;
-  l.total = l.scratch_off + kMaxProdWarps * 2 * kAaScratch * 4;
+  l.bias_off = l.scratch_off + kMaxProdWarps * 2 * kAaScratch * 4;
+  l.total = l.bias_off + kBiasCache * 4;
   return l;
 }
 
@@ -442,8 +457,10 @@ struct EpiAux {           // the one auxiliary input of the plain epilogue: resi
 // Plain epilogue: regular conv, N_total % 16 == 0, no output activation, NAUX auxiliary inputs (residual and/or
 // the old y), and every tensor small enough for 32-bit element offsets (host: a.epi_fast).  Addresses are
 // (uniform 64-bit base) + (32-bit offset), one integer add per access.
-template <int NAUX>
-__device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux& ax0, const EpiAux& ax1, uint32_t tm0,
+// BATCH = items whose auxiliary loads are issued together (2 with 128 registers per thread, 1 in the 80-register
+// snake kernel, which has 8 epilogue warps to hide the latency instead).
+template <int NAUX, int BATCH>
+__device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float* bias_s, const EpiAux& ax0, const EpiAux& ax1, uint32_t tm0,
                                                  int nsub, int slabs, int slab0, int slab_step, int nt, int m_base,
                                                  int len_out, uint32_t ybase) {
   // work items = (slab, sub-tile) pairs, slab-major.  The auxiliary rows of the next item(s) are requested
@@ -467,14 +484,15 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux
       for (int i = 0; i < 16; ++i, off += ax.ld) r[i] = TB200_LDMODE ? __ldcg(p + off) : p[off];
     }
   };
-  float bias[16];   // bias * out_alpha
   auto finish_item = [&](int k, const float (&r0)[16], const float (&r1)[16]) {
     const int sl = k / nsub, sub = k - sl * nsub;
     const int s = slab0 + sl * slab_step;
     const uint32_t n0 = (uint32_t)(nt * a.NT + s * 16);
-    if (sub == 0) {
+    float bias[16];   // bias * out_alpha, cached in shared memory by the whole CTA at kernel start
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bias[i] = a.bias ? __ldg(a.bias + n0 + i) * a.out_alpha : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + 4 * i);
+      bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
     }
     const int m = m_base + sub * kTileM;
     const bool row_ok = m < len_out;
@@ -498,11 +516,18 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const EpiAux
   if constexpr (NAUX == 1) {
     // batches of 2 items: 32 row loads requested back to back, then both items drained (one memory latency per
     // 2 items; one item of look-ahead pays it per item -- measured 3.3 K cycles per 16-column item)
-    for (int k = 0; k < nitems; k += 2) {
-      fetch1(k, ax0, ra);
-      if (k + 1 < nitems) fetch1(k + 1, ax0, rb);
-      finish_item(k, ra, ra);
-      if (k + 1 < nitems) finish_item(k + 1, rb, rb);
+    if constexpr (BATCH == 2) {
+      for (int k = 0; k < nitems; k += 2) {
+        fetch1(k, ax0, ra);
+        if (k + 1 < nitems) fetch1(k + 1, ax0, rb);
+        finish_item(k, ra, ra);
+        if (k + 1 < nitems) finish_item(k + 1, rb, rb);
+      }
+    } else {
+      for (int k = 0; k < nitems; ++k) {
+        fetch1(k, ax0, ra);
+        finish_item(k, ra, ra);
+      }
     }
   } else if constexpr (NAUX == 2) {
     // two inputs (rare: last pair of the 2nd/3rd residual block of a stage): 32 loads per item, no look-ahead
@@ -566,7 +591,8 @@ __device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t t
 // CTAS = resident CTAs per SM: 2 halves the per-CTA registers (64), shared memory and TMEM columns but doubles the
 // independent warps (and scoreboards) that hide global-memory latency -- used for the pointwise staging family.
 template <typename T, bool SNAKE, int CTAS>
-__global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int kWorkerWarps = Roles<SNAKE>::kWorkers, kMmaWarp = Roles<SNAKE>::kMma, kLoadWarp = Roles<SNAKE>::kLoad;
   constexpr int E = ElemTraits<T>::kEpc;
   constexpr bool kTf32 = ElemTraits<T>::kTf32;
   constexpr int kStepK = 2 * E;  // K per tcgen05.mma
@@ -605,6 +631,9 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
     tmem_alloc(tmem_slot, a.tmem_cols);
     tmem_relinquish();
   }
+  float* bias_s = reinterpret_cast<float*>(smem + lay.bias_off);
+  if (a.epi_fast)
+    for (int i = threadIdx.x; i < a.N_total; i += blockDim.x) bias_s[i] = a.bias ? __ldg(a.bias + i) * a.out_alpha : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -830,9 +859,9 @@ __global__ void __launch_bounds__(kThreads, CTAS) conv1d_umma_kernel(const __gri
         const int m_base = t0 + q * 32 + lane;
         const EpiAux axr{a.residual, (uint32_t)rbase, (uint32_t)a.r_ld, 0, a.res_beta};
         const EpiAux axy{a.y, (uint32_t)ybase, (uint32_t)a.y_ld, a.y_f16, 1.0f};
-        if (mode == 2) epilogue_plain<2>(a, axr, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
-        else if (mode == 1) epilogue_plain<1>(a, a.residual ? axr : axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
-        else if (mode == 0) epilogue_plain<0>(a, axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        if (mode == 2) epilogue_plain<2, TB200_SNAKE_EPI_BATCH>(a, bias_s, axr, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        else if (mode == 1) epilogue_plain<1, SNAKE ? TB200_SNAKE_EPI_BATCH : 2>(a, bias_s, a.residual ? axr : axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+        else if (mode == 0) epilogue_plain<0, 2>(a, bias_s, axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
         else epilogue_generic(a, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, ybase, rbase);
         tc_fence_before();
         __syncwarp();
@@ -876,7 +905,7 @@ static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
   const int slots = g_sm_count * CTAS;
   int grid = slots < a.total_tiles ? slots : a.total_tiles;  // persistent: CTAS CTAs per SM
   if (grid < 1) grid = 1;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(a);
+  kern<<<grid, Roles<SNAKE>::kThreads, smem_bytes, stream>>>(a);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -888,7 +917,7 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas) {
   const int tmem_cap = 512 / ctas;
   const int span = a.R - kTileM;  // halo rows (left + right)
   const int epc = 16 / elem_bytes;
-  const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kMaxProdWarps * 2 * kAaScratch * 4 + 256;
+  const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kMaxProdWarps * 2 * kAaScratch * 4 + kBiasCache * 4 + 256;
   const long long w_total = (long long)a.n_chunks * a.chunk_bytes;
   // pass 0 insists on weights resident in shared memory (no per-tile L2 re-streaming), pass 1 allows the ring
   for (int pass = 0; pass < 2; ++pass) {
@@ -968,12 +997,13 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   {
     const long long lim = 1LL << 31;
     const long long y_ext = (long long)a.B * a.y_bs, r_ext = a.residual ? (long long)a.B * a.r_bs : 0;
-    a.epi_fast = a.up == 0 && a.out_act == TB200_OUT_NONE && a.N_total % 16 == 0 &&
+    a.epi_fast = a.up == 0 && a.out_act == TB200_OUT_NONE && a.N_total % 16 == 0 && a.N_total <= kBiasCache &&
                  y_ext < lim && r_ext < lim && a.y_bs >= 0 && a.r_bs >= 0;
   }
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
   // otherwise the epilogue is (6 + 8)
-  a.n_prod = (a.act == TB200_ACT_AA_SNAKEBETA) ? kMaxProdWarps : 6;
+  // snake: 14 producers + 8 epilogue warps (18 + 4 measured slower even for store-only epilogues); pointwise: 6 + 8
+  a.n_prod = snake ? Roles<true>::kWorkers - 8 : 6;
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceTiles * 8 * sizeof(long long)));
@@ -1000,7 +1030,8 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   }
   if (const char* e = getenv(a.act == TB200_ACT_AA_SNAKEBETA ? "TB200_NPROD_SNAKE" : "TB200_NPROD_PW")) {  // tuning knob
     const int v = atoi(e);
-    if (v == 6 || v == 10) a.n_prod = v;
+    const int w = a.act == TB200_ACT_AA_SNAKEBETA ? Roles<true>::kWorkers : Roles<false>::kWorkers;
+    if (v >= 2 && v <= kMaxProdWarps && (w - v == 4 || w - v == 8)) a.n_prod = v;
   }
   const int smem_bytes = ws_layout(a).total;
   if (smem_bytes > g_max_smem / ctas) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
