@@ -82,6 +82,7 @@ struct ElemTraits<float> {
 //  0 producer: a_empty acquired   1 producer: tile staged     2 MMA: a_full acquired   3 MMA: all MMAs issued
 //  4 epilogue: acc_full acquired  5 epilogue: tile drained    6 MMA: acc_empty acquired
 constexpr int kTraceTiles = 96;
+constexpr int kTraceCtas = 160;   // after the tile stamps: elapsed cycles and %smid of every CTA
 __device__ __forceinline__ void trace(const ConvArgs& a, int slot, uint32_t idx) {
   if (a.trace && blockIdx.x == 0 && idx < (uint32_t)kTraceTiles) a.trace[idx * 8 + slot] = clock64();
 }
@@ -610,6 +611,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
   float* scratch = reinterpret_cast<float*>(smem + lay.scratch_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_kernel_start = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -873,6 +875,11 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
 
   tc_fence_before();
   __syncthreads();
+  if (a.trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace[kTraceTiles * 8 + blockIdx.x] = ((long long)smid << 48) | (clock64() - t_kernel_start);
+  }
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
@@ -1006,8 +1013,8 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   a.n_prod = snake ? Roles<true>::kWorkers - 8 : 6;
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
-    if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceTiles * 8 * sizeof(long long)));
-    TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, kTraceTiles * 8 * sizeof(long long), stream));
+    if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long)));
+    TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long), stream));
     a.trace = g_trace;
   }
   a.l2_prefetch = 0;  // measured: next-tile L2 prefetch doubles DRAM reads (lines evicted before use) -- kept as a knob
@@ -1045,7 +1052,7 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
 
 int conv_trace_read(long long* host_out, int n) {
   if (!g_trace) return fail(TB200_E_BADARG, "trace: TB200_TRACE was not set");
-  TB200_CUDA_CHECK(cudaMemcpy(host_out, g_trace, sizeof(long long) * (n < kTraceTiles * 8 ? n : kTraceTiles * 8), cudaMemcpyDeviceToHost));
+  TB200_CUDA_CHECK(cudaMemcpy(host_out, g_trace, sizeof(long long) * (n < kTraceTiles * 8 + kTraceCtas ? n : kTraceTiles * 8 + kTraceCtas), cudaMemcpyDeviceToHost));
   return 0;
 }
 

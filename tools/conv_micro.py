@@ -40,9 +40,13 @@ if os.environ.get("TB200_TRACE"):
     import ctypes
 
     from ims_toucan_prosody_variance_b200 import _lib
-    buf = (ctypes.c_int64 * (96 * 8))()
-    _lib.check(_lib.load().tb200_debug_trace_read(ctypes.cast(buf, ctypes.c_void_p), 96 * 8), "trace")
-    t = torch.tensor(list(buf), dtype=torch.int64).reshape(96, 8)
+    buf = (ctypes.c_int64 * (96 * 8 + 160))()
+    _lib.check(_lib.load().tb200_debug_trace_read(ctypes.cast(buf, ctypes.c_void_p), 96 * 8 + 160), "trace")
+    t = torch.tensor(list(buf)[:96 * 8], dtype=torch.int64).reshape(96, 8)
+    per_cta = [(v & ((1 << 48) - 1), v >> 48) for v in list(buf)[96 * 8:] if v]
+    cyc = sorted(c for c, _ in per_cta)
+    print(f"per-CTA elapsed cycles over {len(cyc)} CTAs: min {cyc[0]} median {cyc[len(cyc) // 2]} max {cyc[-1]}")
+    print("slowest CTAs (cycles, smid):", sorted(per_cta, reverse=True)[:6], " fastest:", sorted(per_cta)[:4])
     base = int(t[:, :7][t[:, :7] > 0].min())
     print("tile  a_empty  staged | a_full  mma_issued  acc_empty(mma) | acc_full  drained   (clock cycles since first stamp)")
     for i in range(24):
