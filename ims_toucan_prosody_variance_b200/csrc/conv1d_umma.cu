@@ -51,12 +51,15 @@ namespace tb200 {
 #ifndef TB200_SNAKE_EPI_BATCH
 #define TB200_SNAKE_EPI_BATCH 1
 #endif
+#ifndef TB200_PW_WORKERS
+#define TB200_PW_WORKERS 14
+#endif
 #ifndef TB200_SNAKE_WORKERS
 #define TB200_SNAKE_WORKERS 22
 #endif
 template <bool SNAKE>
 struct Roles {
-  static constexpr int kWorkers = SNAKE ? TB200_SNAKE_WORKERS : 14;
+  static constexpr int kWorkers = SNAKE ? TB200_SNAKE_WORKERS : TB200_PW_WORKERS;
   static constexpr int kMma = kWorkers;
   static constexpr int kLoad = kWorkers + 1;
   static constexpr int kThreads = (kWorkers + 2) * 32;
@@ -349,9 +352,96 @@ __device__ __forceinline__ void load8(const void* x, bool f16, long long idx, fl
   }
 }
 
+// One (32-channel block, row segment) task.  EDGE segments (near the utterance's ends) read x with clamped indices
+// (replicate padding of the 2x up-sampler), clamp the snake output index to [0, 2 len) (replicate padding of the
+// down-sampler) and emit zeros outside [0, len); interior segments are compiled without any of these branches.
+template <typename T, bool EDGE>
+__device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row, int c, int t_lo, int t_beg, int t_end,
+                                                int len, T* dst) {
+  constexpr int E = ElemTraits<T>::kEpc;
+  const int ts = (t_beg - 9) & ~7;        // first ingested step, 16-byte aligned
+  const float ea = __expf(__ldg(a.alpha + c));
+  const float ib = 1.0f / (__expf(__ldg(a.beta + c)) + 1e-9f);
+  float xw[8], sv[16], cur[8], n1[8], n2[8];
+  auto loadx = [&](int base, float (&r)[8]) {
+    if (!EDGE || (base >= 0 && base + 8 <= len)) {
+      load8(a.x, a.x_f16, row + base, r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = load_x(a.x, a.x_f16, row + min(max(base + i, 0), len - 1));
+    }
+  };
+  float s_first = 0.f, s_last = 0.f;
+  if (EDGE && t_beg < 3) {                // s[0]: what the down-sampler sees left of the utterance
+    float u = 0.f;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) u = fmaf(load_x(a.x, a.x_f16, row + min(max(q - 3, 0), len - 1)), c_aa_filter[11 - 2 * q], u);
+    u *= 2.f;
+    const float z = __sinf(u * ea);
+    s_first = fmaf(ib * z, z, u);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xw[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+  loadx(ts, cur);
+  loadx(ts + 8, n1);
+  // one 8-step block; CHECK = false once every step both produces a pair and emits an output row
+  auto block8 = [&](auto check_tag, int base) {
+    constexpr bool CHECK = decltype(check_tag)::value;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = base + j;
+      xw[j] = cur[j];
+      if (!CHECK || n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
+        float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          u0 = fmaf(xw[(j + 2 + q) & 7], c_aa_filter[11 - 2 * q], u0);   // x[n-6+q]
+          u1 = fmaf(xw[(j + 3 + q) & 7], c_aa_filter[10 - 2 * q], u1);   // x[n-5+q]
+        }
+        u0 *= 2.f;
+        u1 *= 2.f;
+        const float z0 = __sinf(u0 * ea), z1 = __sinf(u1 * ea);
+        float s0 = fmaf(ib * z0, z0, u0), s1 = fmaf(ib * z1, z1, u1);
+        if constexpr (EDGE) {
+          const int pi = n - 3;
+          if (pi < 0) s0 = s1 = s_first;
+          else if (pi >= len) s0 = s1 = s_last;
+          else s_last = s1;
+        }
+        sv[2 * ((j + 5) & 7)] = s0;
+        sv[2 * ((j + 5) & 7) + 1] = s1;
+      }
+      const int t = n - 6;
+      if (!CHECK || (t >= t_beg && t < t_end)) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
+          o0 = fmaf(c_aa_filter[k], sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
+          o1 = fmaf(c_aa_filter[k + 1], sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
+        }
+        float o = o0 + o1;
+        if (EDGE && (t < 0 || t >= len)) o = 0.f;
+        dst[(long long)(t - t_lo) * E] = to_operand<T>(o);
+      }
+    }
+  };
+  for (int base = ts; base - 6 < t_end; base += 8) {
+    loadx(base + 16, n2);
+    if (!EDGE && base - 6 >= t_beg && base + 1 < t_end) block8(std::false_type{}, base);
+    else block8(std::true_type{}, base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cur[i] = n1[i];
+      n1[i] = n2[i];
+    }
+  }
+}
+
 template <typename T>
-__device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int t_lo, int cb0, int ncb, int nseg, T* smA,
-                                                 int pw, int lane) {
+__device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int t_lo, int cb0, int ncb, int nseg, int len,
+                                                 T* smA, int pw, int lane) {
   constexpr int E = ElemTraits<T>::kEpc;
   const int R = a.R;
   const int seg_rows = (R + nseg - 1) / nseg;
@@ -364,61 +454,15 @@ __device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int
     const int cl = cb * 32 + lane;          // channel inside this staged panel
     const int c = cb0 * 32 + cl;            // absolute input channel
     const int t_beg = t_lo + r_beg, t_end = t_lo + r_end;
-    const int ts = (t_beg - 9) & ~7;        // first ingested step, 16-byte aligned
-    const long long row = xb + (long long)c * a.x_ld;
-    const float ea = __expf(__ldg(a.alpha + c));
-    const float ib = 1.0f / (__expf(__ldg(a.beta + c)) + 1e-9f);
     T* dst = smA + ((long long)(cl / E) * R) * E + (cl % E);
-
-    float xw[8], sv[16], cur[8], n1[8], n2[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) xw[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sv[i] = 0.f;
-    load8(a.x, a.x_f16, row + ts, cur);
-    load8(a.x, a.x_f16, row + ts + 8, n1);
-    // one 8-step block; CHECK = false once every step both produces a pair and emits an output row
-    auto block8 = [&](auto check_tag, int base) {
-      constexpr bool CHECK = decltype(check_tag)::value;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = base + j;
-        xw[j] = cur[j];
-        if (!CHECK || n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
-          float u0 = 0.f, u1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            u0 = fmaf(xw[(j + 2 + q) & 7], c_aa_filter[11 - 2 * q], u0);   // x[n-6+q]
-            u1 = fmaf(xw[(j + 3 + q) & 7], c_aa_filter[10 - 2 * q], u1);   // x[n-5+q]
-          }
-          u0 *= 2.f;
-          u1 *= 2.f;
-          const float z0 = __sinf(u0 * ea), z1 = __sinf(u1 * ea);
-          sv[2 * ((j + 5) & 7)] = fmaf(ib * z0, z0, u0);
-          sv[2 * ((j + 5) & 7) + 1] = fmaf(ib * z1, z1, u1);
-        }
-        const int t = n - 6;
-        if (!CHECK || (t >= t_beg && t < t_end)) {
-          float o0 = 0.f, o1 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
-            o0 = fmaf(c_aa_filter[k], sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
-            o1 = fmaf(c_aa_filter[k + 1], sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
-          }
-          dst[(long long)(t - t_lo) * E] = to_operand<T>(o0 + o1);
-        }
-      }
-    };
-    for (int base = ts; base - 6 < t_end; base += 8) {
-      load8(a.x, a.x_f16, row + base + 16, n2);  // look-ahead stays inside the utterance: see `interior`
-      if (base - 6 >= t_beg && base + 1 < t_end) block8(std::false_type{}, base);
-      else block8(std::true_type{}, base);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        cur[i] = n1[i];
-        n1[i] = n2[i];
-      }
+    if (t_beg >= len || t_end <= 0) {       // segment entirely outside the utterance: the conv's zero padding
+      for (int t = t_beg; t < t_end; ++t) dst[(long long)(t - t_lo) * E] = to_operand<T>(0.f);
+      continue;
     }
+    const long long row = xb + (long long)c * a.x_ld;
+    const bool edge = (((t_beg - 9) & ~7) < 0) || (t_end + 32 > len);   // warp-uniform
+    if (edge) aa_channel_task<T, true>(a, row, c, t_lo, t_beg, t_end, len, dst);
+    else aa_channel_task<T, false>(a, row, c, t_lo, t_beg, t_end, len, dst);
   }
 }
 
@@ -683,9 +727,9 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
           T* smA = reinterpret_cast<T*>(smem + lay.a_off + buf * a.a_bytes);
           const int g0 = pn * groups_per_panel;
           if constexpr (SNAKE) {
-            // fast path: whole staged range (plus filter reach and load look-ahead) inside the utterance
-            const bool interior = a.aa_fast && (t_lo - 16 >= 0) && (t_lo + a.R + 32 <= len);
-            if (interior) {
+            // lane = channel streaming path (edge segments clamp their reads inside); the generic per-row path only
+            // when its alignment / channel-count preconditions fail
+            if (a.aa_fast) {
               const int ncb = groups_per_panel * E / 32;
               // row segments per 32-channel block: tasks = ncb * nseg is a multiple of the producer warps (balanced rounds)
               int gcd = ncb, r2 = a.n_prod;
@@ -694,7 +738,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                 gcd = r2;
                 r2 = tmp;
               }
-              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, a.n_prod / gcd, smA, warp, lane);
+              stage_aa_channel<T>(a, b, t_lo, g0 * E / 32, ncb, a.n_prod / gcd, len, smA, warp, lane);
             } else {
               const UmmaStore<T> st{smA, a.R};
               stage_aa_snake<E, true>(a, b, t_lo, a.R, g0, groups_per_panel, len, st, scratch, warp, a.n_prod, lane);
@@ -1010,7 +1054,7 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
   // otherwise the epilogue is (6 + 8)
   // snake: 14 producers + 8 epilogue warps (18 + 4 measured slower even for store-only epilogues); pointwise: 6 + 8
-  a.n_prod = snake ? Roles<true>::kWorkers - 8 : 6;
+  a.n_prod = snake ? Roles<true>::kWorkers - 8 : Roles<false>::kWorkers - 8;
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long)));
