@@ -129,3 +129,17 @@ def test_transposed_wide_multi_ntile(cuda, prec):
 def test_single_tap_tiny(cuda):
     for prec in ("fp32", "f16", "tf32"):
         _run(cuda, prec, B=1, Cin=16, Cout=16, K=1, dil=1, L=5)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_zero_length_utterance_in_batch(cuda, prec):
+    # an empty utterance inside a batch is skipped: nothing read, nothing written
+    _run(cuda, prec, B=3, Cin=32, Cout=32, K=7, dil=3, L=200, lens=[200, 0, 64], act=1, slope=0.1, residual=True)
+    _run(cuda, prec, B=3, Cin=32, Cout=32, K=3, dil=1, L=200, lens=[0, 200, 3], snake=True)
+
+
+def test_snake_edges_short_and_unaligned_lengths(cuda):
+    # utterance lengths around the 8-step block size and the filter reach of the anti-aliased snake
+    for n in (1, 2, 5, 7, 8, 9, 15, 17, 31, 33):
+        _run(cuda, "f16", B=2, Cin=32, Cout=32, K=3, dil=1, L=40, lens=[40, n], snake=True, seed=n)
+    _run(cuda, "f16", B=2, Cin=64, Cout=64, K=11, dil=5, L=700, lens=[700, 513], snake=True, residual=True)

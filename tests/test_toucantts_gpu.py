@@ -164,3 +164,34 @@ def test_long_form_external_prosody(cuda):
     assert torch.allclose(pitch.cpu(), ref_p, atol=1e-5) and torch.allclose(energy.cpu(), ref_e, atol=1e-5)
     assert mel.shape == (2 * (int(ref_d.sum()) // 2), 80)
     assert torch.isfinite(mel).all()
+
+
+def test_all_zero_durations_rescue_and_tiny_utterance(cuda):
+    """LengthRegulator.py:52-53: an utterance whose durations sum to 0 gets one frame per phoneme; a 3-phoneme
+    utterance (shorter than every conv kernel) still goes through the whole path."""
+    from oracle import factory, restate
+    model, fsd = _engine(cuda, "fp32")
+    text = factory.make_phoneme_tensor(6, 21)
+    emb = factory.make_utterance_embedding(21)
+    zeros = torch.zeros(6, dtype=torch.int64)
+    p = torch.ones(6, 1)
+    noise = torch.randn((1, 80, 6), generator=torch.Generator().manual_seed(1))
+    r = model.synthesize_batch(text.unsqueeze(0).to(cuda), torch.tensor([6]), gold_durations=zeros.unsqueeze(0),
+                               gold_pitch=p.unsqueeze(0), gold_energy=p.unsqueeze(0), utterance_embedding=emb.unsqueeze(0).to(cuda),
+                               lang_ids=torch.tensor([12]), noise=noise)
+    assert int(r["frames"][0]) == 6 and r["durations"][0, :6].tolist() == [1] * 6
+    with torch.inference_mode():
+        ref = restate.toucantts_forward(fsd, text, emb, lang_id=12, durations=zeros.clone(), pitch=p.clone(), energy=p.clone(),
+                                        noise=noise[0])
+    assert _rel_l1(r["mel_ncl"][0, :, :6].t().cpu(), ref["mel"]) < 1e-3
+
+    text3 = factory.make_phoneme_tensor(3, 22)
+    with torch.inference_mode():
+        ref3 = restate.toucantts_forward(fsd, text3, emb, lang_id=12, generator=torch.Generator().manual_seed(2))
+    f3 = int(ref3["durations"].sum())
+    noise3 = torch.randn((1, 80, f3), generator=torch.Generator().manual_seed(2))
+    r3 = model.synthesize_batch(text3.unsqueeze(0).to(cuda), torch.tensor([3]), utterance_embedding=emb.unsqueeze(0).to(cuda),
+                                lang_ids=torch.tensor([12]), noise=noise3)
+    assert torch.equal(r3["durations"][0, :3].cpu(), ref3["durations"])
+    m = 2 * (f3 // 2)
+    assert _rel_l1(r3["mel_ncl"][0, :, :m].t().cpu(), ref3["mel"]) < 1e-3
