@@ -1054,7 +1054,10 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
   // otherwise the epilogue is (6 + 8)
   // snake: 14 producers + 8 epilogue warps (18 + 4 measured slower even for store-only epilogues); pointwise: 6 + 8
-  a.n_prod = snake ? Roles<true>::kWorkers - 8 : Roles<false>::kWorkers - 8;
+  // pointwise: 6 + 8 when the epilogue fetches auxiliary rows, 10 + 4 when it only stores (staging is then the long
+  // pole: measured 30 K vs 8 K cycles per tile)
+  a.n_prod = snake ? Roles<true>::kWorkers - 8
+                   : Roles<false>::kWorkers - ((a.residual || a.accumulate || !a.epi_fast) ? 8 : 4);
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long)));

@@ -63,3 +63,26 @@ def test_golden_vocoder_fixture(cuda, tmp_path):
         wave = model(mel.to(cuda)).cpu()
         snr = restate.snr_db(wave, golden[kind].float())
         assert snr >= 40.0, f"{kind}: SNR vs reference fixture {snr:.1f} dB"
+
+
+def test_forward_is_cuda_graph_capturable(cuda, tmp_path):
+    """The C ABI enqueues on the caller's stream and never synchronises: a whole generator forward can be captured
+    in a CUDA graph and replayed (workspaces are allocated by the warm-up call)."""
+    from oracle import factory, restate
+    model, fsd = _make("hifigan", "f16", cuda, str(tmp_path))
+    mel = factory.make_mel(2, 16, seed=5).to(cuda)
+    lens = torch.tensor([16, 9], dtype=torch.int32, device=cuda)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eager = model.forward_batch(mel, lens).clone()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = model.forward_batch(mel, lens)
+    mel.copy_(factory.make_mel(2, 16, seed=6).to(cuda))      # new input, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = restate.hifigan_forward(fsd, mel[0, :, :16].cpu())
+    assert restate.snr_db(out[0, :16 * 384].cpu(), ref) >= 40.0
+    assert not torch.equal(out, eager)
