@@ -799,6 +799,8 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     if (lane == 0) {
       const uint32_t idesc = make_instr_desc(a.NT, kTf32);
       const uint32_t lbo_a = a.R * 16, lbo_b = a.NT * 16;
+      const uint32_t desc_hi = smem_desc_hi(128);
+      const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;   // descriptor units (16 bytes) per K step
       const uint32_t smW_u = smem_u32(smW);
       uint32_t ai = 0, ac = 0, cc = 0;
       bool first_tile = true;
@@ -839,11 +841,18 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
                 const uint32_t a_base = a_row + (uint32_t)(kcl * (a.KC / E)) * lbo_a;
                 const uint32_t fresh = (pn == 0 && j == 0 && kcl == 0) ? 0u : 1u;
+                // descriptors advance by 32-bit adds on their start-address field (the single issuing thread is
+                // instruction bound: ~30 dependent integer ops per MMA measured 160-290 cycles per MMA)
+                const uint32_t a_lo0 = smem_desc_lo(a_base, lbo_a), b_lo0 = smem_desc_lo(b_base, lbo_b);
+                const int nks = a.KC / kStepK;
                 for (int sub = 0; sub < nsub; ++sub) {
-                  for (int ks = 0; ks < a.KC / kStepK; ++ks) {
-                    const uint64_t da = make_smem_desc(a_base + (uint32_t)(sub * kTileM) * 16u + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-                    const uint64_t db = make_smem_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-                    umma_ss<kTf32>(acc_col + (uint32_t)(sub * a.NT), da, db, idesc, (ks == 0) ? fresh : 1u);
+                  uint32_t a_lo = a_lo0 + (uint32_t)(sub * kTileM), b_lo = b_lo0;   // 16 bytes per row -> +1 per row
+                  const uint32_t d_col = acc_col + (uint32_t)(sub * a.NT);
+                  umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
+                  for (int ks = 1; ks < nks; ++ks) {
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
+                    umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
                   }
                 }
                 if (!a.resident) umma_commit(w_empty + slot);
