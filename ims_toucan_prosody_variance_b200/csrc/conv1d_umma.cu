@@ -65,7 +65,7 @@ struct Roles {
   static constexpr int kThreads = (kWorkers + 2) * 32;
 };
 constexpr int kMaxProdWarps = 18;
-constexpr int kBiasCache = 512;             // floats of (bias * out_alpha) cached in shared memory for the plain epilogue
+constexpr int kBiasCache = 2048;            // floats of (bias * out_alpha) cached in shared memory for the plain epilogue
 constexpr int kMaxRing = 64;
 
 template <typename T>
@@ -515,6 +515,7 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float*
   float* yf = reinterpret_cast<float*>(a.y);
   __half* yh = reinterpret_cast<__half*>(a.y);
   const uint32_t y_ld = (uint32_t)a.y_ld;
+  const bool relu = a.out_act == TB200_OUT_RELU;
   auto fetch1 = [&](int k, const EpiAux& ax, float (&r)[16]) {
     const int sl = k / nsub, sub = k - sl * nsub;
     const uint32_t n0 = (uint32_t)(nt * a.NT + (slab0 + sl * slab_step) * 16);
@@ -549,6 +550,7 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float*
 #pragma unroll
     for (int i = 0; i < 16; ++i, yo += y_ld) {
       float val = fmaf(__uint_as_float(v[i]), a.out_alpha, bias[i]);
+      if (relu) val = fmaxf(val, 0.f);   // alpha * relu(x) == relu(alpha * x) for alpha >= 0 (host-checked)
       if constexpr (NAUX >= 1) val = fmaf(ax0.beta, r0[i], val);
       if constexpr (NAUX >= 2) val = fmaf(ax1.beta, r1[i], val);
       if (row_ok) {
@@ -803,6 +805,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
       const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;   // descriptor units (16 bytes) per K step
       const uint32_t smW_u = smem_u32(smW);
       uint32_t ai = 0, ac = 0, cc = 0;
+      long long w_wait = 0;   // cycles the issuer spent waiting for streamed weight chunks (trace only)
       bool first_tile = true;
       uint32_t a_buf_cur = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -835,7 +838,9 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                   if (first_tile) mbar_wait(w_full + slot, 0);
                 } else {
                   slot = cc % a.ring_slots;
+                  const long long tw = a.trace ? clock64() : 0;
                   mbar_wait(w_full + slot, (cc / a.ring_slots) & 1);
+                  if (a.trace) w_wait += clock64() - tw;
                 }
                 tc_fence_after();
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
@@ -862,6 +867,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
           }
           umma_commit(acc_full + abuf);
           trace(a, 3, ac);
+          if (a.trace && blockIdx.x == 0 && ac < (uint32_t)kTraceTiles) a.trace[ac * 8 + 7] = w_wait;   // cumulative
         }
         first_tile = false;
       }
@@ -1057,7 +1063,8 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   {
     const long long lim = 1LL << 31;
     const long long y_ext = (long long)a.B * a.y_bs, r_ext = a.residual ? (long long)a.B * a.r_bs : 0;
-    a.epi_fast = a.up == 0 && a.out_act == TB200_OUT_NONE && a.N_total % 16 == 0 && a.N_total <= kBiasCache &&
+    a.epi_fast = a.up == 0 && (a.out_act == TB200_OUT_NONE || (a.out_act == TB200_OUT_RELU && a.out_alpha >= 0.f)) &&
+                 a.N_total % 16 == 0 && a.N_total <= kBiasCache &&
                  y_ext < lim && r_ext < lim && a.y_bs >= 0 && a.r_bs >= 0;
   }
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),

@@ -143,3 +143,31 @@ def test_snake_edges_short_and_unaligned_lengths(cuda):
     for n in (1, 2, 5, 7, 8, 9, 15, 17, 31, 33):
         _run(cuda, "f16", B=2, Cin=32, Cout=32, K=3, dil=1, L=40, lens=[40, n], snake=True, seed=n)
     _run(cuda, "f16", B=2, Cin=64, Cout=64, K=11, dil=5, L=700, lens=[700, 513], snake=True, residual=True)
+
+
+@pytest.mark.parametrize("prec", ["f16", "tf32"])
+def test_wide_linear_relu_and_scaled_residual(cuda, prec):
+    # the acoustic model's FFN pair: 192 -> 1536 with ReLU, 1536 -> 192 scaled by 0.5 plus residual
+    from ims_toucan_prosody_variance_b200 import ops
+    from ims_toucan_prosody_variance_b200._lib import OUT_RELU
+    g = torch.Generator().manual_seed(4)
+    B, L, lens = 3, 200, [200, 77, 130]
+    x = torch.randn(B, 192, L, generator=g)
+    w1, b1 = torch.randn(1536, 192, generator=g) / 192 ** 0.5, torch.randn(1536, generator=g) * 0.1
+    w2, b2 = torch.randn(192, 1536, generator=g) / 1536 ** 0.5, torch.randn(192, generator=g) * 0.1
+    l1 = ops.ConvLayer(w1.to(cuda), b1.to(cuda), precision=prec)
+    l2 = ops.ConvLayer(w2.to(cuda), b2.to(cuda), precision=prec)
+    xd = x.to(cuda)
+    h = torch.zeros(B, 1536, L, device=cuda)
+    y = xd.clone()
+    lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    l1(xd, lt, h, out_act=OUT_RELU)
+    l2(h, lt, y, out_alpha=0.5, residual=y)
+    torch.cuda.synchronize()
+    for b, n in enumerate(lens):
+        hb = torch.relu(torch.einsum("oc,cl->ol", w1, x[b, :, :n]) + b1[:, None])
+        ref = x[b, :, :n] + 0.5 * (torch.einsum("oc,cl->ol", w2, hb) + b2[:, None])
+        got = y[b, :, :n].cpu()
+        rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        assert rel < 2e-3, f"{prec} b={b} rel rms err {rel:.3e}"
+        assert torch.equal(y[b, :, n:].cpu(), x[b, :, n:])

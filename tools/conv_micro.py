@@ -51,4 +51,5 @@ if os.environ.get("TB200_TRACE"):
     print("tile  a_empty  staged | a_full  mma_issued  acc_empty(mma) | acc_full  drained   (clock cycles since first stamp)")
     for i in range(24):
         r = [int(v) - base if int(v) > 0 else -1 for v in t[i, :7]]
-        print(f"{i:4d} {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[6]:8d} | {r[4]:8d} {r[5]:8d}   stage {r[1]-r[0]:6d}  mma-issue {r[3]-r[2]:6d}  mma->accfull {r[4]-r[3]:6d}  drain {r[5]-r[4]:6d}")
+        ww = int(t[i, 7]) - (int(t[i - 1, 7]) if i else 0)
+        print(f"{i:4d} {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[6]:8d} | {r[4]:8d} {r[5]:8d}   stage {r[1]-r[0]:6d}  mma-issue {r[3]-r[2]:6d}  (weight wait {ww:6d})  mma->accfull {r[4]-r[3]:6d}  drain {r[5]-r[4]:6d}")
