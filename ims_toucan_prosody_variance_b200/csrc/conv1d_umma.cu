@@ -352,6 +352,16 @@ __device__ __forceinline__ void load8(const void* x, bool f16, long long idx, fl
   }
 }
 
+// kaiser_sinc_filter1d(cutoff 0.25, half-width 0.3, 12 taps) of alias_free_torch as compile-time immediates for the
+// streaming path (FFMA with an immediate operand: no constant-bank reloads in the inner loop).  Same values as the
+// host-computed c_aa_filter: float(double closed form).
+__device__ __forceinline__ constexpr float aa_tap(int k) {
+  constexpr float t[12] = {2.028966555e-03f, 9.389463812e-03f, -2.554346435e-02f, -5.765737593e-02f, 1.285726130e-01f,
+                           4.432097971e-01f, 4.432097971e-01f, 1.285726130e-01f, -5.765737593e-02f, -2.554346435e-02f,
+                           9.389463812e-03f, 2.028966555e-03f};
+  return t[k];
+}
+
 // One (32-channel block, row segment) task.  EDGE segments (near the utterance's ends) read x with clamped indices
 // (replicate padding of the 2x up-sampler), clamp the snake output index to [0, 2 len) (replicate padding of the
 // down-sampler) and emit zeros outside [0, len); interior segments are compiled without any of these branches.
@@ -375,8 +385,7 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
   if (EDGE && t_beg < 3) {                // s[0]: what the down-sampler sees left of the utterance
     float u = 0.f;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) u = fmaf(load_x(a.x, a.x_f16, row + min(max(q - 3, 0), len - 1)), c_aa_filter[11 - 2 * q], u);
-    u *= 2.f;
+    for (int q = 0; q < 6; ++q) u = fmaf(load_x(a.x, a.x_f16, row + min(max(q - 3, 0), len - 1)), 2.f * aa_tap(11 - 2 * q), u);
     const float z = __sinf(u * ea);
     s_first = fmaf(ib * z, z, u);
   }
@@ -389,6 +398,7 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
   // one 8-step block; CHECK = false once every step both produces a pair and emits an output row
   auto block8 = [&](auto check_tag, int base) {
     constexpr bool CHECK = decltype(check_tag)::value;
+    T* drow = dst + (long long)(base - 6 - t_lo) * E;   // row of step j = 0 (t = base - 6); +E per step
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = base + j;
@@ -397,11 +407,9 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
         float u0 = 0.f, u1 = 0.f;
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-          u0 = fmaf(xw[(j + 2 + q) & 7], c_aa_filter[11 - 2 * q], u0);   // x[n-6+q]
-          u1 = fmaf(xw[(j + 3 + q) & 7], c_aa_filter[10 - 2 * q], u1);   // x[n-5+q]
+          u0 = fmaf(xw[(j + 2 + q) & 7], 2.f * aa_tap(11 - 2 * q), u0);   // x[n-6+q]; the x2 of the up-sampler is exact
+          u1 = fmaf(xw[(j + 3 + q) & 7], 2.f * aa_tap(10 - 2 * q), u1);   // x[n-5+q]
         }
-        u0 *= 2.f;
-        u1 *= 2.f;
         const float z0 = __sinf(u0 * ea), z1 = __sinf(u1 * ea);
         float s0 = fmaf(ib * z0, z0, u0), s1 = fmaf(ib * z1, z1, u1);
         if constexpr (EDGE) {
@@ -418,12 +426,12 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
-          o0 = fmaf(c_aa_filter[k], sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
-          o1 = fmaf(c_aa_filter[k + 1], sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
+          o0 = fmaf(aa_tap(k), sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
+          o1 = fmaf(aa_tap(k + 1), sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
         }
         float o = o0 + o1;
         if (EDGE && (t < 0 || t >= len)) o = 0.f;
-        dst[(long long)(t - t_lo) * E] = to_operand<T>(o);
+        drow[j * E] = to_operand<T>(o);
       }
     }
   };
