@@ -135,15 +135,17 @@ __global__ void __launch_bounds__(256) group_norm_kernel(
 //   h = BatchNorm1d(eval)(h);  y = h * sigmoid(h)                (Swish)
 // grid (time tiles of 256, C, B), block 256.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDwTile = 256;
+constexpr int kDwThreads = 256;
+constexpr int kDwPer = 4;                       // consecutive outputs per thread (register sliding window)
+constexpr int kDwTile = kDwThreads * kDwPer;    // 1024 time steps per CTA
 constexpr int kDwMaxK = 63;
 
-__global__ void __launch_bounds__(kDwTile) glu_dwconv_kernel(
+__global__ void __launch_bounds__(kDwThreads) glu_dwconv_kernel(
     const float* __restrict__ x, long long x_bs, int x_ld, float* __restrict__ y, long long y_bs, int y_ld,
     const int* __restrict__ len, int C, int L_max, const float* __restrict__ w, const float* __restrict__ bias, int K,
     const float* __restrict__ bn_mean, const float* __restrict__ bn_var, const float* __restrict__ bn_gamma,
     const float* __restrict__ bn_beta, float bn_eps) {
-  __shared__ float h[kDwTile + kDwMaxK];
+  __shared__ __align__(16) float h[kDwTile + kDwMaxK + 9];
   __shared__ float wk[kDwMaxK + 1];
   const int b = blockIdx.z, c = blockIdx.y;
   const int L = utt_len(len, b, L_max);
@@ -152,24 +154,46 @@ __global__ void __launch_bounds__(kDwTile) glu_dwconv_kernel(
   const int pad = (K - 1) / 2;
   const float* xa = x + (long long)b * x_bs + (long long)c * x_ld;
   const float* xg = xa + (long long)C * x_ld;
-  for (int i = threadIdx.x; i < kDwTile + K - 1; i += kDwTile) {
+  for (int i = threadIdx.x; i < kDwTile + kDwMaxK + 9; i += kDwThreads) {
     const int t = t0 - pad + i;
     float v = 0.f;
-    if (t >= 0 && t < L) {
+    if (i < kDwTile + K - 1 && t >= 0 && t < L) {
       const float a = __ldg(xa + t), g = __ldg(xg + t);
       v = a * (1.0f / (1.0f + expf(-g)));
     }
     h[i] = v;
   }
-  if (threadIdx.x < K) wk[threadIdx.x] = __ldg(w + (long long)c * K + threadIdx.x);
+  if (threadIdx.x <= kDwMaxK) wk[threadIdx.x] = threadIdx.x < K ? __ldg(w + (long long)c * K + threadIdx.x) : 0.f;  // zero padded
   __syncthreads();
-  const int t = t0 + threadIdx.x;
-  if (t >= L) return;
-  float acc = 0.f;
-  for (int j = 0; j < K; ++j) acc = fmaf(wk[j], h[threadIdx.x + j], acc);
-  acc += __ldg(bias + c);
-  const float n = (acc - __ldg(bn_mean + c)) * rsqrtf(__ldg(bn_var + c) + bn_eps) * __ldg(bn_gamma + c) + __ldg(bn_beta + c);
-  y[(long long)b * y_bs + (long long)c * y_ld + t] = n * (1.0f / (1.0f + expf(-n)));
+  const int o0 = threadIdx.x * kDwPer;            // first output of this thread inside the tile
+  if (t0 + o0 >= L) return;
+  float acc[kDwPer];
+#pragma unroll
+  for (int i = 0; i < kDwPer; ++i) acc[i] = 0.f;
+  // 8-value register window over h[o0 + 4q .. o0 + 4q + 7]: four taps per 16-byte shared-memory load (conflict
+  // free: consecutive lanes read consecutive 16-byte groups), 16 FMAs per load
+  float4 lo = *reinterpret_cast<const float4*>(h + o0);
+  for (int q = 0; q * 4 < K; ++q) {
+    const float4 hi = *reinterpret_cast<const float4*>(h + o0 + 4 * q + 4);
+    const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float wj = wk[4 * q + jj];
+#pragma unroll
+      for (int i = 0; i < kDwPer; ++i) acc[i] = fmaf(wj, win[i + jj], acc[i]);
+    }
+    lo = hi;
+  }
+  const float bc = __ldg(bias + c), mu = __ldg(bn_mean + c), rs = rsqrtf(__ldg(bn_var + c) + bn_eps);
+  const float ga = __ldg(bn_gamma + c), be = __ldg(bn_beta + c);
+  float* yo = y + (long long)b * y_bs + (long long)c * y_ld + t0 + o0;
+#pragma unroll
+  for (int i = 0; i < kDwPer; ++i) {
+    if (t0 + o0 + i < L) {
+      const float n = (acc[i] + bc - mu) * rs * ga + be;
+      yo[i] = n * (1.0f / (1.0f + expf(-n)));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,32 +412,61 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long in_bs, 
 //   unsqueeze: y[b][c][2 tau + s] = x[b][s*C + c][tau],  tau < len2[b]    (len = squeezed lengths)
 __global__ void squeeze2_kernel(const float* __restrict__ x, long long x_bs, int x_ld, float* __restrict__ y,
                                 long long y_bs, int y_ld, const int* __restrict__ len, int C, int L_max, int inverse) {
+  // a thread moves 4 consecutive positions of the UNSQUEEZED axis = 2 positions of each squeezed row:
+  // 16-byte accesses on the unsqueezed side, 8-byte accesses on the two squeezed rows, all coalesced
   const int b = blockIdx.z, c = blockIdx.y;
   const int L = utt_len(len, b, L_max);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = inverse ? 2 * L : 2 * (L / 2);   // valid unsqueezed positions (len = squeezed / unsqueezed lengths)
+  if (i >= n) return;
+  const long long un = (long long)b * (inverse ? y_bs : x_bs) + (long long)c * (inverse ? y_ld : x_ld) + i;
+  const long long s0 = (long long)b * (inverse ? x_bs : y_bs) + (long long)c * (inverse ? x_ld : y_ld) + (i >> 1);
+  const long long s1 = s0 + (long long)C * (inverse ? x_ld : y_ld);
+  const bool full = i + 4 <= n && (((inverse ? y_ld : x_ld) | (inverse ? x_ld : y_ld)) & 3) == 0 &&
+                    (((inverse ? y_bs : x_bs) | (inverse ? x_bs : y_bs)) & 3) == 0;
   if (!inverse) {
-    const int L2 = L / 2;  // len = unsqueezed lengths
-    if (i >= 2 * L2) return;
-    const int tau = i >> 1, s = i & 1;
-    y[(long long)b * y_bs + (long long)(s * C + c) * y_ld + tau] = __ldg(x + (long long)b * x_bs + (long long)c * x_ld + i);
+    if (full && ((reinterpret_cast<uintptr_t>(x + un) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y + s0) & 7) == 0) &&
+        ((reinterpret_cast<uintptr_t>(y + s1) & 7) == 0)) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + un));
+      *reinterpret_cast<float2*>(y + s0) = make_float2(v.x, v.z);
+      *reinterpret_cast<float2*>(y + s1) = make_float2(v.y, v.w);
+    } else {
+      for (int k = 0; k < 4 && i + k < n; ++k) y[((k & 1) ? s1 : s0) + (k >> 1)] = __ldg(x + un + k);
+    }
   } else {
-    if (i >= 2 * L) return;   // len = squeezed lengths
-    const int tau = i >> 1, s = i & 1;
-    y[(long long)b * y_bs + (long long)c * y_ld + i] = __ldg(x + (long long)b * x_bs + (long long)(s * C + c) * x_ld + tau);
+    if (full && ((reinterpret_cast<uintptr_t>(y + un) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x + s0) & 7) == 0) &&
+        ((reinterpret_cast<uintptr_t>(x + s1) & 7) == 0)) {
+      const float2 e = __ldg(reinterpret_cast<const float2*>(x + s0)), o = __ldg(reinterpret_cast<const float2*>(x + s1));
+      *reinterpret_cast<float4*>(y + un) = make_float4(e.x, o.x, e.y, o.y);
+    } else {
+      for (int k = 0; k < 4 && i + k < n; ++k) y[un + k] = __ldg(x + ((k & 1) ? s1 : s0) + (k >> 1));
+    }
   }
 }
 
 // WaveNet gate (wavenet.py:29-35, 102-111): y[c] = tanh(a[c]) * sigmoid(a[c + H]).
+// VEC = 4: one 16-byte load per operand row and one 16-byte store per thread (pitches and bases 16-byte aligned).
+template <int VEC>
 __global__ void wn_gate_kernel(const float* __restrict__ a, long long a_bs, int a_ld, float* __restrict__ y, long long y_bs,
                                int y_ld, const int* __restrict__ len, int Hc, int L_max) {
   const int b = blockIdx.z, c = blockIdx.y;
   const int L = utt_len(len, b, L_max);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (t >= L) return;
-  const float* ab = a + (long long)b * a_bs + t;
-  const float ta = tanhf(__ldg(ab + (long long)c * a_ld));
-  const float sg = 1.0f / (1.0f + expf(-__ldg(ab + (long long)(c + Hc) * a_ld)));
-  y[(long long)b * y_bs + (long long)c * y_ld + t] = ta * sg;
+  const float* ta = a + (long long)b * a_bs + (long long)c * a_ld + t;
+  const float* sa = ta + (long long)Hc * a_ld;
+  float* yo = y + (long long)b * y_bs + (long long)c * y_ld + t;
+  if (VEC == 4 && t + 4 <= L) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(ta)), g = __ldg(reinterpret_cast<const float4*>(sa));
+    float4 o;
+    o.x = tanhf(u.x) * (1.0f / (1.0f + expf(-g.x)));
+    o.y = tanhf(u.y) * (1.0f / (1.0f + expf(-g.y)));
+    o.z = tanhf(u.z) * (1.0f / (1.0f + expf(-g.z)));
+    o.w = tanhf(u.w) * (1.0f / (1.0f + expf(-g.w)));
+    *reinterpret_cast<float4*>(yo) = o;
+  } else {
+    for (int i = 0; i < VEC && t + i < L; ++i) yo[i] = tanhf(__ldg(ta + i)) * (1.0f / (1.0f + expf(-__ldg(sa + i))));
+  }
 }
 
 // The three elementwise steps that close one reversed flow block (Glow.py:260-263, 116-128, 30-32):
@@ -567,7 +620,7 @@ int tb200_glu_dwconv(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64
   if (B <= 0 || C <= 0 || L_max <= 0 || K < 1 || K > kDwMaxK || !(K & 1)) return fail(TB200_E_BADARG, "glu_dwconv: K must be odd and <= %d", kDwMaxK);
   if (C > 65535 || B > 65535) return fail(TB200_E_BADARG, "glu_dwconv: grid too large");
   dim3 grid((L_max + kDwTile - 1) / kDwTile, C, B);
-  glu_dwconv_kernel<<<grid, kDwTile, 0, static_cast<cudaStream_t>(stream)>>>(x, x_bs, x_ld, y, y_bs, y_ld, len, C, L_max, w, bias,
+  glu_dwconv_kernel<<<grid, kDwThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, x_bs, x_ld, y, y_bs, y_ld, len, C, L_max, w, bias,
                                                                               K, bn_mean, bn_var, bn_gamma, bn_beta, bn_eps);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -625,8 +678,9 @@ int tb200_squeeze2(const float* x, int64_t x_bs, int32_t x_ld, float* y, int64_t
                    int32_t B, int32_t C, int32_t L_max, int32_t inverse, void* stream) {
   if (!x || !y) return fail(TB200_E_BADARG, "squeeze2: null pointer");
   if (B <= 0 || C <= 0 || L_max <= 0) return fail(TB200_E_BADARG, "squeeze2: bad shape");
-  dim3 grid;
-  if (int rc = ew_grid(inverse ? 2 * L_max : L_max, C, B, grid)) return rc;
+  if (C > 65535 || B > 65535) return fail(TB200_E_BADARG, "elementwise: grid too large");
+  const int n = inverse ? 2 * L_max : L_max;     // unsqueezed positions, 4 per thread
+  dim3 grid((n + 1023) / 1024, C, B);
   squeeze2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_bs, x_ld, y, y_bs, y_ld, len, C, L_max, inverse);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -636,9 +690,17 @@ int tb200_wn_gate(const float* a, int64_t a_bs, int32_t a_ld, float* y, int64_t 
                   int32_t B, int32_t hidden, int32_t L_max, void* stream) {
   if (!a || !y) return fail(TB200_E_BADARG, "wn_gate: null pointer");
   if (B <= 0 || hidden <= 0 || L_max <= 0) return fail(TB200_E_BADARG, "wn_gate: bad shape");
-  dim3 grid;
-  if (int rc = ew_grid(L_max, hidden, B, grid)) return rc;
-  wn_gate_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, a_bs, a_ld, y, y_bs, y_ld, len, hidden, L_max);
+  if (hidden > 65535 || B > 65535) return fail(TB200_E_BADARG, "elementwise: grid too large");
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && a_ld % 4 == 0 && y_ld % 4 == 0 &&
+                   a_bs % 4 == 0 && y_bs % 4 == 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vec) {
+    dim3 grid((L_max + 1023) / 1024, hidden, B);
+    wn_gate_kernel<4><<<grid, 256, 0, s>>>(a, a_bs, a_ld, y, y_bs, y_ld, len, hidden, L_max);
+  } else {
+    dim3 grid((L_max + 255) / 256, hidden, B);
+    wn_gate_kernel<1><<<grid, 256, 0, s>>>(a, a_bs, a_ld, y, y_bs, y_ld, len, hidden, L_max);
+  }
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

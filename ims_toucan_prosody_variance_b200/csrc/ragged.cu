@@ -112,8 +112,10 @@ __global__ void variance_edit_kernel(float* __restrict__ curve, const float* __r
 }
 
 // LengthRegulator.py:57-61 (repeat_interleave) + utils.py:475-494 (pad) + InferenceToucanTTS.py:230-232.
-// grid (frame tiles, B); each CTA resolves 128 frame->phoneme indices by binary search over the
-// inclusive prefix sums, then streams the channels: coalesced writes, L1-resident gathers.
+// grid (frame tiles of 512, B); a thread resolves the phoneme of 4 consecutive frames (one binary search over the
+// inclusive prefix sums, then a short forward scan), and streams the channels: 16-byte coalesced stores, L1-resident
+// gathers (consecutive frames mostly share a phoneme).
+constexpr int kLrPer = 4;
 __global__ void __launch_bounds__(128) length_regulate_kernel(
     const float* __restrict__ enc, long long enc_bs, int enc_ld, const float* __restrict__ pitch,
     const float* __restrict__ energy, int pe_ld, const float* __restrict__ wp, const float* __restrict__ bp,
@@ -121,35 +123,56 @@ __global__ void __launch_bounds__(128) length_regulate_kernel(
     const int* __restrict__ text_len, const int* __restrict__ frames, int C, float* __restrict__ out, long long out_bs,
     int out_ld, int* __restrict__ f2p, int f2p_ld) {
   const int b = blockIdx.y;
-  const int f = blockIdx.x * 128 + threadIdx.x;
+  const int f0 = (blockIdx.x * 128 + threadIdx.x) * kLrPer;
   const int F = frames[b];
-  if (blockIdx.x * 128 >= F) return;
+  if (f0 >= F) return;
   const int T = text_len[b];
   const int* cm = cum + (long long)b * cum_ld;
-  int idx = 0;
-  float pv = 0.f, ev = 0.f;
-  const bool valid = f < F;
-  if (valid) {
-    int lo = 0, hi = T;  // first i with cum[i] > f
+  int idx[kLrPer];
+  float pv[kLrPer], ev[kLrPer];
+  {
+    int lo = 0, hi = T;  // first i with cum[i] > f0
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (__ldg(cm + mid) <= f) lo = mid + 1;
+      if (__ldg(cm + mid) <= f0) lo = mid + 1;
       else hi = mid;
     }
-    idx = lo;
-    if (f2p) f2p[(long long)b * f2p_ld + f] = idx;
-    if (pitch) pv = pitch[(long long)b * pe_ld + idx];
-    if (energy) ev = energy[(long long)b * pe_ld + idx];
+    idx[0] = lo;
+#pragma unroll
+    for (int k = 1; k < kLrPer; ++k) {
+      int i = idx[k - 1];
+      while (i < T - 1 && __ldg(cm + i) <= f0 + k) ++i;   // zero-duration phonemes are skipped
+      idx[k] = i;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kLrPer; ++k) {
+    const bool ok = f0 + k < F;
+    if (!ok) idx[k] = idx[0];
+    if (f2p && ok) f2p[(long long)b * f2p_ld + f0 + k] = idx[k];
+    pv[k] = pitch ? pitch[(long long)b * pe_ld + idx[k]] : 0.f;
+    ev[k] = energy ? energy[(long long)b * pe_ld + idx[k]] : 0.f;
   }
   const float* eb = enc + (long long)b * enc_bs;
-  float* ob = out + (long long)b * out_bs;
-  if (valid) {
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-      float v = __ldg(eb + (long long)c * enc_ld + idx);
-      if (pitch) v += fmaf(pv, __ldg(wp + c), __ldg(bp + c));
-      if (energy) v += fmaf(ev, __ldg(we + c), __ldg(be + c));
-      ob[(long long)c * out_ld + f] = v;
+  float* ob = out + (long long)b * out_bs + f0;
+  const bool vec = f0 + kLrPer <= F && (out_ld & 3) == 0 && (out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {   // 8 channels x 4 gathers in flight per thread
+    const float* er = eb + (long long)c * enc_ld;
+    float v[kLrPer];
+#pragma unroll
+    for (int k = 0; k < kLrPer; ++k) {
+      v[k] = __ldg(er + idx[k]);
+      if (pitch) v[k] += fmaf(pv[k], __ldg(wp + c), __ldg(bp + c));
+      if (energy) v[k] += fmaf(ev[k], __ldg(we + c), __ldg(be + c));
+    }
+    float* orow = ob + (long long)c * out_ld;
+    if (vec) {
+      *reinterpret_cast<float4*>(orow) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kLrPer; ++k)
+        if (f0 + k < F) orow[k] = v[k];
     }
   }
 }
@@ -193,7 +216,7 @@ int tb200_length_regulate(const float* enc, int64_t enc_bs, int32_t enc_ld, cons
   if (!enc || !cum || !text_len || !frames || !out) return fail(TB200_E_BADARG, "length_regulate: null pointer");
   if ((pitch && (!wp || !bp)) || (energy && (!we || !be))) return fail(TB200_E_BADARG, "length_regulate: missing embed weights");
   if (B <= 0 || C <= 0 || F_max <= 0) return fail(TB200_E_BADARG, "length_regulate: bad shape");
-  dim3 grid((F_max + 127) / 128, B);
+  dim3 grid((F_max + 128 * kLrPer - 1) / (128 * kLrPer), B);
   length_regulate_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       enc, enc_bs, enc_ld, pitch, energy, pe_ld, wp, bp, we, be, cum, cum_ld, text_len, frames, C, out, out_bs, out_ld,
       frame_to_phone, f2p_ld);
