@@ -993,13 +993,22 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas) {
   const int epc = 16 / elem_bytes;
   const int fixed = (2 * kMaxRing + 8) * 8 + 16 + kMaxProdWarps * 2 * kAaScratch * 4 + kBiasCache * 4 + 256;
   const long long w_total = (long long)a.n_chunks * a.chunk_bytes;
-  // pass 0 insists on weights resident in shared memory (no per-tile L2 re-streaming), pass 1 allows the ring
+  // pass 0 insists on weights resident in shared memory and all channels staged at once (first fit, largest tile).
+  // pass 1 (streamed weights and / or channel panels) scores every candidate: most rows per weight pass first (every
+  // extra sub-tile divides the weight bytes re-read from L2 per output row), then double-buffered staging (measured:
+  // a double-buffered panel that is re-staged per N tile beats a single-buffered full tile on the acoustic model's
+  // GEMMs), then the fewest staging passes.
+  long long best_key = -1;
+  ConvArgs best = a;
   for (int pass = 0; pass < 2; ++pass) {
     for (int a_bufs = 2; a_bufs >= 1; --a_bufs) {
       for (int S = TB200_MAX_S; S >= 1; S >>= 1) {
         if (S > 1 && ((S / 2) * kTileM >= rows_max)) continue;  // tile longer than the data
-        if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < 2 * g_sm_count * ctas) continue;  // keep SMs busy
-        if (S > 1 && 2 * S * a.NT > tmem_cap) continue;         // two accumulator buffers must fit in TMEM
+        // keep the SMs busy: at least two tiles per SM with resident weights; four with streamed weights (single-
+        // buffered accumulators lose the MMA / epilogue overlap, so a ragged last wave costs more: measured on the
+        // acoustic model's GEMMs, where 1.3 waves of double-height tiles were 8 % slower than 2.2 waves of single ones)
+        if (S > 1 && (long long)a.B * ((rows_max + S * kTileM - 1) / (S * kTileM)) < (pass == 0 ? 2 : 4) * g_sm_count * ctas) continue;
+        if (S > 1 && pass == 0 && 2 * S * a.NT > tmem_cap) continue;   // resident weights: insist on two accumulator buffers
         if (S * a.NT > tmem_cap) continue;
         const int acc_bufs = 2 * S * a.NT <= tmem_cap ? 2 : 1;
         const int R = S * kTileM + span;
@@ -1010,24 +1019,39 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas) {
           if (budget < 2LL * a.chunk_bytes) continue;
           const bool resident = w_total <= budget && a.n_chunks <= kMaxRing;
           if (pass == 0 && (!resident || n_panels > 1)) continue;
-          a.S = S; a.a_bufs = a_bufs; a.acc_bufs = acc_bufs; a.n_panels = n_panels; a.R = R; a.a_bytes = a_bytes;
+          ConvArgs c = a;
+          c.S = S; c.a_bufs = a_bufs; c.acc_bufs = acc_bufs; c.n_panels = n_panels; c.R = R; c.a_bytes = a_bytes;
           if (resident) {
-            a.resident = 1;
-            a.ring_slots = a.n_chunks;
+            c.resident = 1;
+            c.ring_slots = c.n_chunks;
           } else {
-            a.resident = 0;
-            long long slots = budget / a.chunk_bytes;
-            a.ring_slots = (int)(slots > 8 ? 8 : slots);
+            c.resident = 0;
+            long long slots = budget / c.chunk_bytes;
+            c.ring_slots = (int)(slots > 8 ? 8 : slots);
           }
           int cols = 32;
-          while (cols < acc_bufs * S * a.NT) cols <<= 1;
-          a.tmem_cols = cols;
-          a.tiles_per_utt = (rows_max + S * kTileM - 1) / (S * kTileM);
-          a.total_tiles = a.tiles_per_utt * a.B;
-          return 0;
+          while (cols < acc_bufs * S * c.NT) cols <<= 1;
+          c.tmem_cols = cols;
+          c.tiles_per_utt = (rows_max + S * kTileM - 1) / (S * kTileM);
+          c.total_tiles = c.tiles_per_utt * c.B;
+          if (pass == 0) {
+            a = c;
+            return 0;
+          }
+          const long long stagings = n_panels > 1 ? a.n_ntiles : 1;
+          const long long key = (((TB200_MAX_S - S) * 4 + (2 - a_bufs)) * 64 + stagings) * 4096 + n_panels;   // smaller is better
+          if (best_key < 0 || key < best_key) {
+            best_key = key;
+            best = c;
+          }
+          break;  // more panels of the same (a_bufs, S) are never better
         }
       }
     }
+  }
+  if (best_key >= 0) {
+    a = best;
+    return 0;
   }
   return fail(TB200_E_NOSMEM, "conv1d: no tiling of Cin=%d Cout=%d taps=%d fits in shared memory", a.Cin, a.Cout, a.ntaps);
 }
