@@ -15,14 +15,17 @@
 //   D: fp32 in TMEM, double buffered; epilogue = tcgen05.ld -> bias / activation / scale / residual /
 //     accumulate -> coalesced NCL stores (a warp writes 32 consecutive time steps of one channel).
 //
-// Warp roles (one persistent CTA per SM, 16 warps = 4 per SM sub-partition, 128 registers each):
+// Warp roles (one persistent CTA per SM; W worker warps, then the MMA warp and the loader warp):
 //   warps 0 .. nP-1   producers : stage A[buf] (double buffered), arrive a_full
-//   warps nP .. 13    epilogue  : drain accumulator buffer, arrive acc_empty  (4 or 8 warps; any 4 consecutive
+//   warps nP .. W-1   epilogue  : drain accumulator buffer, arrive acc_empty  (4 or 8 warps; any 4 consecutive
 //                                 warps cover the four TMEM lane quarters)
-//   warp  14          MMA issuer: one elected thread issues tcgen05.mma, commits to a_empty / acc_full / w_empty
-//   warp  15          weight loader (TMA bulk copies)
-// nP = 10 when the prologue is the anti-aliased snake (staging is the SIMT-heavy side), 6 otherwise.
-// so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+//   warp  W           MMA issuer: one elected thread issues tcgen05.mma, commits to a_empty / acc_full / w_empty
+//   warp  W+1         weight loader (TMA bulk copies)
+// so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.  Two kernels per operand type:
+//   pointwise prologues: W = 14 (16 warps, 128 registers); nP = 6 (+8 epilogue) when the epilogue fetches residual /
+//                        accumulate rows, 10 (+4) when it only stores
+//   snake prologue:      W = 22 (24 warps, 80 registers); nP = 14 (+8): the staging is FMA-issue bound
+// TB200_TRACE=1 records clock64() stamps of every role per tile (tools/conv_micro.py prints the timeline).
 //
 // Tiles past an utterance's length are skipped, rows past it are staged as zeros (the zero padding a
 // batch-1 reference call sees).
