@@ -1067,25 +1067,13 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   if (rc) return rc;
   const int elem_bytes = p->precision == TB200_PREC_F16 ? 2 : 4;
   const int rows_max = p->L_in_max + (a.up > 0 ? 1 : 0);
-  // pointwise staging family: try two resident CTAs per SM first (more independent warps in flight); only when
-  // the weights stay resident in the smaller shared-memory share, else one CTA per SM
+  // One persistent CTA per SM.  (Two resident CTAs per SM -- 64 registers, half the shared memory and TMEM each -- were
+  // measured 1.6-2.7x slower: the register cap spills, and with the L1 carved out for shared memory a spill is a DRAM
+  // round trip.  plan() and the kernel template keep the CTAS parameter.)
   const bool snake = a.act == TB200_ACT_AA_SNAKEBETA;
-  int ctas = 1;
-  {
-    int want = 1;   // two CTAs per SM measured slower (the 64-register cap spills); kept as a knob
-    if (const char* e = getenv("TB200_CTAS")) want = atoi(e) == 2 ? 2 : 1;   // tuning knob
-    if (want == 2) {
-      ConvArgs t = a;
-      if (plan(t, elem_bytes, rows_max, 2) == 0 && t.resident && t.n_panels == 1) {
-        a = t;
-        ctas = 2;
-      }
-    }
-  }
-  if (ctas == 1) {
-    rc = plan(a, elem_bytes, rows_max, 1);
-    if (rc) return rc;
-  }
+  constexpr int ctas = 1;
+  rc = plan(a, elem_bytes, rows_max, ctas);
+  if (rc) return rc;
   // lane=channel snake staging: 16-byte loads need an aligned base / pitch and 32-channel blocks
   const int align = a.x_f16 ? 8 : 4;
   a.aa_fast = (a.act == TB200_ACT_AA_SNAKEBETA) && (a.Cin % 32 == 0) && ((a.Cin_pad / a.n_panels) % 32 == 0) &&
@@ -1140,12 +1128,9 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   }
   const int smem_bytes = ws_layout(a).total;
   if (smem_bytes > g_max_smem / ctas) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
-  if (p->precision == TB200_PREC_F16) {
-    if (snake) return launch_t<__half, true, 1>(a, smem_bytes, stream);
-    return ctas == 2 ? launch_t<__half, false, 2>(a, smem_bytes, stream) : launch_t<__half, false, 1>(a, smem_bytes, stream);
-  }
-  if (snake) return launch_t<float, true, 1>(a, smem_bytes, stream);
-  return ctas == 2 ? launch_t<float, false, 2>(a, smem_bytes, stream) : launch_t<float, false, 1>(a, smem_bytes, stream);
+  if (p->precision == TB200_PREC_F16)
+    return snake ? launch_t<__half, true, ctas>(a, smem_bytes, stream) : launch_t<__half, false, ctas>(a, smem_bytes, stream);
+  return snake ? launch_t<float, true, ctas>(a, smem_bytes, stream) : launch_t<float, false, ctas>(a, smem_bytes, stream);
 }
 
 int conv_trace_read(long long* host_out, int n) {
