@@ -32,14 +32,22 @@ class _Frontend:
         return factory.make_phoneme_tensor(n, seed)
 
 
-def test_text_to_wave_batch_vs_oracle(cuda, tmp_path):
+@pytest.mark.parametrize("kind", ["hifigan", "bigvgan"])
+def test_text_to_wave_batch_vs_oracle(cuda, tmp_path, kind):
     import ims_toucan_prosody_variance_b200 as tb
     from oracle import factory, restate
     tpath, vpath, tfsd, vfsd = _models(cuda, tmp_path)
     ckpt = torch.load(tpath)
     tts = tb.ToucanTTS(weights=ckpt["model"], precision="fp32").to(cuda)
     tts.store_inverse_all()
-    voc = tb.HiFiGANGenerator(vpath, precision="f16").to(cuda)
+    if kind == "bigvgan":
+        bsd = factory.make_state_dict("bigvgan", 1234)
+        vpath = os.path.join(tmp_path, "bvoc.pt")
+        torch.save({"generator": bsd}, vpath)
+        vfsd = restate.fold_weight_norm(bsd)
+        voc = tb.BigVGAN(vpath, precision="f16").to(cuda)
+    else:
+        voc = tb.HiFiGANGenerator(vpath, precision="f16").to(cuda)
     voc.remove_weight_norm()
     eng = tb.TextToWave(tts, voc)
     lens = [17, 9, 26]
@@ -54,7 +62,7 @@ def test_text_to_wave_batch_vs_oracle(cuda, tmp_path):
     for i in range(3):
         with torch.inference_mode():
             ref = restate.toucantts_forward(tfsd, texts[i], embs[i], lang_id=12, noise=noise[i, :, :int(r["frames_host"][i])])
-            ref_wave = restate.hifigan_forward(vfsd, ref["mel"].t())
+            ref_wave = (restate.bigvgan_forward if kind == "bigvgan" else restate.hifigan_forward)(vfsd, ref["mel"].t())
         assert torch.equal(r["durations"][i, :lens[i]].cpu(), ref["durations"])
         assert int(wlen[i]) == ref_wave.numel()
         snr = restate.snr_db(wave[i, :int(wlen[i])].cpu(), ref_wave)

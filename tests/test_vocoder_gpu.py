@@ -86,3 +86,27 @@ def test_forward_is_cuda_graph_capturable(cuda, tmp_path):
     ref = restate.hifigan_forward(fsd, mel[0, :, :16].cpu())
     assert restate.snr_db(out[0, :16 * 384].cpu(), ref) >= 40.0
     assert not torch.equal(out, eager)
+
+
+@pytest.mark.parametrize("kind", ["bigvgan", "hifigan"])
+def test_full_size_batch_is_batch_invariant(cuda, tmp_path, kind):
+    """BASELINE.json configs[1] at full size (64 mels x 500 frames): every utterance of the batch matches its own
+    batch-1 call (size-independent property: no leakage across utterances or tiles), output finite and in (-1, 1).
+    Not bit-equal at this size: with streamed weights the number of sub-tiles per CTA depends on the tile count, and
+    interleaving MMAs over several accumulators changes the fp32 rounding of the sums at the 1e-7 level (measured per
+    launch: tools/conv_invariance.py); every fp16 operand rounding downstream turns a fraction of those into 1-ulp
+    flips (tools/batch_vs_single.py).  The two runs must still agree well inside the 40 dB bound."""
+    from oracle import factory, restate
+    model, fsd = _make(kind, "f16", cuda, str(tmp_path))
+    mel = factory.make_mel(64, 500, seed=100).to(cuda)
+    lens = torch.full((64,), 500, dtype=torch.int32, device=cuda)
+    wave = model.forward_batch(mel, lens).clone()
+    assert wave.shape == (64, 500 * 384) and torch.isfinite(wave).all() and float(wave.abs().max()) <= 1.0
+    for b in (0, 37, 63):
+        single = model.forward_batch(mel[b:b + 1].contiguous(), lens[b:b + 1])
+        snr = restate.snr_db(wave[b].cpu(), single[0].cpu())
+        assert snr >= 50.0, f"utterance {b}: batched vs batch-1 SNR {snr:.1f} dB"
+    # a slice of one utterance against the oracle (CPU): the first 40 frames see the same left context
+    ref = (restate.bigvgan_forward if kind == "bigvgan" else restate.hifigan_forward)(fsd, mel[5, :, :80].cpu())
+    got = model.forward_batch(mel[5:6, :, :80].contiguous(), torch.tensor([80], dtype=torch.int32, device=cuda))[0].cpu()
+    assert restate.snr_db(got, ref) >= 40.0
