@@ -256,6 +256,10 @@ class UtteranceCloner:
         start = torch.zeros([sil_start * 3], device=speech.device)
         end = torch.zeros([sil_end * 3], device=speech.device)
         cloned = torch.cat((start, speech, end), dim=0)
-        if filename is not None:
-            _write_pcm16(filename, float2pcm(cloned).cpu().numpy(), SAMPLE_RATE)
+        if filename is not None:   # UtteranceCloner.py:165-166 writes with soundfile; PCM16 WAV when it is not installed
+            try:
+                import soundfile
+                soundfile.write(file=filename, data=cloned.cpu().numpy(), samplerate=SAMPLE_RATE)
+            except ImportError:
+                _write_pcm16(filename, float2pcm(cloned).cpu().numpy(), SAMPLE_RATE)
         return cloned.cpu().numpy()
