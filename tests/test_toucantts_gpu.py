@@ -195,3 +195,37 @@ def test_all_zero_durations_rescue_and_tiny_utterance(cuda):
     assert torch.equal(r3["durations"][0, :3].cpu(), ref3["durations"])
     m = 2 * (f3 // 2)
     assert _rel_l1(r3["mel_ncl"][0, :, :m].t().cpu(), ref3["mel"]) < 1e-3
+
+
+def test_single_speaker_single_language_variant(cuda):
+    """ToucanTTSInterface.py:53-62 falls back to lang_embs=None / utt_embed_dim=None checkpoints: predictors then use
+    plain LayerNorm (VariancePredictor.py:42-47) and the encoder has no embedding projection."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from ims_toucan_prosody_variance_b200 import layouts
+    from oracle import factory, restate
+    lay, alias = layouts.toucantts_layout(utt_embed_dim=None, lang_embs=None)
+    full = factory.make_state_dict("toucantts", 1234)
+    g = torch.Generator().manual_seed(11)
+    sd = {}
+    for k, shape in lay.items():
+        if k in alias:
+            sd[k] = sd[alias[k]]
+        elif k in full and tuple(full[k].shape) == tuple(shape):
+            sd[k] = full[k].clone()
+        elif k.endswith("norms.0.weight") or ".norms." in k and k.endswith(".weight"):
+            sd[k] = torch.ones(shape) + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[k] = 0.1 * torch.randn(shape, generator=g)
+    model = tb.ToucanTTS(weights=sd, utt_embed_dim=None, lang_embs=None, precision="fp32").to(cuda)
+    model.store_inverse_all()
+    text = factory.make_phoneme_tensor(17, 8)
+    fsd = restate.fold_weight_norm(sd)
+    with torch.inference_mode():
+        ref = restate.toucantts_forward(fsd, text, None, lang_id=None, generator=torch.Generator().manual_seed(5))
+    frames = int(ref["durations"].sum())
+    assert frames >= 2
+    noise = torch.randn((1, 80, frames), generator=torch.Generator().manual_seed(5))
+    r = model.synthesize_batch(text.unsqueeze(0).to(cuda), torch.tensor([17]), noise=noise)
+    assert torch.equal(r["durations"][0, :17].cpu(), ref["durations"])
+    m = 2 * (frames // 2)
+    assert _rel_l1(r["mel_ncl"][0, :, :m].t().cpu(), ref["mel"]) < 1e-3
