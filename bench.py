@@ -97,7 +97,7 @@ class ClockSampler:
         return out
 
 
-def build_generator(kind, precision, device):
+def build_generator(kind, precision, device, activation_dtype="f32"):
     import ims_toucan_prosody_variance_b200 as tb
     from oracle import factory  # weights factory only (state_dict values); not on the timed path
     sd = factory.make_state_dict(kind, 1234)
@@ -105,7 +105,7 @@ def build_generator(kind, precision, device):
         path = os.path.join(td, "g.pt")
         torch.save({"generator": sd}, path)
         cls = tb.BigVGAN if kind == "bigvgan" else tb.HiFiGANGenerator
-        model = cls(path, precision=precision).to(device)
+        model = cls(path, precision=precision, activation_dtype=activation_dtype).to(device)
     model.remove_weight_norm()
     return model, sd
 
@@ -161,7 +161,7 @@ def workload_config(args):
     return {"workload": f"{'BigVGAN' if args.vocoder == 'bigvgan' else 'HiFiGAN'} generator alone: batch {args.batch} "
                         f"synthetic 80-bin mels x {args.frames} frames -> 24 kHz wave (per GPU)",
             "batch_per_gpu": args.batch, "frames": args.frames, "vocoder": args.vocoder,
-            "operand_precision": args.precision, "weights": "random-init (oracle.factory seed 1234)",
+            "operand_precision": args.precision, "residual_stream": args.activations, "weights": "random-init (oracle.factory seed 1234)",
             "l2": "working set per step (>6 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--acoustic-precision", default="tf32", choices=["tf32", "f16", "fp32"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--activations", default="f32", choices=["f32", "f16"], help="storage type of the vocoder residual stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.batch_given = args.batch is not None
@@ -351,7 +352,7 @@ def main():
 
     from ims_toucan_prosody_variance_b200 import ops
     from oracle import factory
-    model, sd = build_generator(args.vocoder, args.precision, dev)
+    model, sd = build_generator(args.vocoder, args.precision, dev, args.activations)
     mel_host = factory.make_mel(args.batch, args.frames, seed=100 + rank).pin_memory()
     mel_dev = mel_host.to(dev)
     lengths = torch.full((args.batch,), args.frames, dtype=torch.int32)

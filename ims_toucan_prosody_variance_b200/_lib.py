@@ -24,7 +24,7 @@ class Conv1dParams(ctypes.Structure):
         ("C_out", c_int), ("K", c_int), ("dilation", c_int), ("pad", c_int), ("transposed_stride", c_int),
         ("w_packed", c_void_p), ("bias", c_void_p), ("precision", c_int),
         ("act", c_int), ("act_slope", c_float), ("act_alpha", c_void_p), ("act_beta", c_void_p),
-        ("out_act", c_int), ("out_alpha", c_float), ("residual", c_void_p), ("r_bs", c_int64), ("r_ld", c_int),
+        ("out_act", c_int), ("out_alpha", c_float), ("residual", c_void_p), ("r_dtype", c_int), ("r_bs", c_int64), ("r_ld", c_int),
         ("res_beta", c_float), ("accumulate", c_int),
         ("y", c_void_p), ("y_dtype", c_int), ("y_bs", c_int64), ("y_ld", c_int),
     ]

@@ -103,7 +103,7 @@ int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a) {
   a.KC = g.KC; a.n_kchunks = g.n_kchunks; a.n_chunks = g.n_chunks;
   a.chunk_bytes = static_cast<int>(g.chunk_elems * g.elem_bytes);
   a.act = p->act; a.slope = p->act_slope;
-  a.x_f16 = p->x_dtype == TB200_F16; a.y_f16 = p->y_dtype == TB200_F16;
+  a.x_f16 = p->x_dtype == TB200_F16; a.y_f16 = p->y_dtype == TB200_F16; a.r_f16 = p->r_dtype == TB200_F16;
   a.out_act = p->out_act; a.out_alpha = p->out_alpha; a.res_beta = p->res_beta; a.accumulate = p->accumulate;
   const int rows_max = p->L_in_max + (up > 0 ? 1 : 0);
   a.tiles_per_utt = (rows_max + kTileM - 1) / kTileM;

@@ -908,8 +908,8 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         const int nt0 = (ntile - nb * a.tiles_per_utt) * rows_tile;
         const int nlen = a.len_in ? __ldg(a.len_in + nb) : a.L_in_max;
         if (nt0 < nlen) {
-          const int esz = a.residual ? 4 : (a.y_f16 ? 2 : 4);
-          const char* base = a.residual ? reinterpret_cast<const char*>(a.residual) + (long long)nb * a.r_bs * 4
+          const int esz = a.residual ? (a.r_f16 ? 2 : 4) : (a.y_f16 ? 2 : 4);
+          const char* base = a.residual ? reinterpret_cast<const char*>(a.residual) + (long long)nb * a.r_bs * esz
                                         : reinterpret_cast<const char*>(a.y) + (long long)nb * a.y_bs * esz;
           const int ld = a.residual ? a.r_ld : a.y_ld;
           const int my_ch = ((a.NT / 16 - slab0 + slab_step - 1) / slab_step) * 16;   // channels this warp will drain
@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         const int slabs = a.NT / 16;
         const uint32_t tm0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * a.S * a.NT);
         const int m_base = t0 + q * 32 + lane;
-        const EpiAux axr{a.residual, (uint32_t)rbase, (uint32_t)a.r_ld, 0, a.res_beta};
+        const EpiAux axr{a.residual, (uint32_t)rbase, (uint32_t)a.r_ld, a.r_f16, a.res_beta};
         const EpiAux axy{a.y, (uint32_t)ybase, (uint32_t)a.y_ld, a.y_f16, 1.0f};
         if (mode == 2) epilogue_plain<2, TB200_SNAKE_EPI_BATCH>(a, bias_s, axr, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
         else if (mode == 1) epilogue_plain<1, SNAKE ? TB200_SNAKE_EPI_BATCH : 2>(a, bias_s, a.residual ? axr : axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);

@@ -13,7 +13,7 @@ struct ConvArgs {
   const void* x;
   const int* len_in;
   void* y;
-  const float* residual;
+  const void* residual;
   const float* bias;
   const float* alpha;
   const float* beta;
@@ -35,7 +35,7 @@ struct ConvArgs {
   int resident;           // all blocks fit: load once per CTA
   int act;
   float slope;
-  int x_f16, y_f16;
+  int x_f16, y_f16, r_f16;
   int out_act;
   float out_alpha, res_beta;
   int accumulate;
@@ -238,7 +238,9 @@ __device__ __forceinline__ float finish(float acc, const ConvArgs& a, int co, lo
   if (a.out_act == TB200_OUT_TANH) v = tanhf(v);
   else if (a.out_act == TB200_OUT_RELU) v = fmaxf(v, 0.f);
   v *= a.out_alpha;
-  if (a.residual) v = fmaf(a.res_beta, __ldg(a.residual + ridx), v);
+  if (a.residual)
+    v = fmaf(a.res_beta, a.r_f16 ? __half2float(reinterpret_cast<const __half*>(a.residual)[ridx])
+                                 : __ldg(reinterpret_cast<const float*>(a.residual) + ridx), v);
   if (a.accumulate)
     v += a.y_f16 ? __half2float(reinterpret_cast<const __half*>(a.y)[yidx]) : reinterpret_cast<const float*>(a.y)[yidx];
   return v;

@@ -82,11 +82,11 @@ class ConvLayer:
         p.act_beta = beta.data_ptr() if beta is not None else None
         p.out_act, p.out_alpha = out_act, out_alpha
         if residual is not None:
-            if residual.dtype != torch.float32 or residual.stride(2) != 1:
-                raise _lib.EngineError("conv1d: residual must be fp32 NCL")
-            p.residual, p.r_bs, p.r_ld = residual.data_ptr(), residual.stride(0), residual.stride(1)
+            if residual.stride(2) != 1:
+                raise _lib.EngineError("conv1d: residual must be NCL with contiguous rows")
+            p.residual, p.r_dtype, p.r_bs, p.r_ld = residual.data_ptr(), _dtype_code(residual), residual.stride(0), residual.stride(1)
         else:
-            p.residual, p.r_bs, p.r_ld = None, 0, 0
+            p.residual, p.r_dtype, p.r_bs, p.r_ld = None, F32, 0, 0
         p.res_beta, p.accumulate = res_beta, int(accumulate)
         p.y, p.y_dtype, p.y_bs, p.y_ld = out.data_ptr(), _dtype_code(out), out.stride(0), out.stride(1)
         if self.out_len(p.L_in_max) > out.shape[2]:

@@ -30,8 +30,11 @@ class _GeneratorBase(torch.nn.Module):
 
     upsample_scales = (8, 6, 4, 2)
 
-    def _init_engine(self, precision):
+    def _init_engine(self, precision, activation_dtype="f32"):
+        if activation_dtype not in ("f32", "f16") or (activation_dtype == "f16" and precision != "f16"):
+            raise ops._lib.EngineError("activation_dtype must be 'f32', or 'f16' together with precision='f16'")
         self.precision = precision
+        self.activation_dtype = activation_dtype   # storage type of the residual stream in HBM
         self._packed = None
         self._buffers_cache = {}
 
@@ -88,13 +91,17 @@ class _GeneratorBase(torch.nn.Module):
         ws = self._buffers_cache.get(key)
         if ws is None:
             self._buffers_cache.clear()
-            ws = {"h": torch.zeros((b, self.channels, _pad4(frames)), dtype=torch.float32, device=dev)}
+            # residual stream: fp32 (default) or fp16 (activation_dtype="f16": halves the HBM bytes per element; every
+            # value is rounded to 11 bits once more per layer -- measured SNR in tests/test_vocoder_gpu.py)
+            sdt = torch.float16 if self.activation_dtype == "f16" else torch.float32
+            pad = _pad8 if sdt == torch.float16 else _pad4
+            ws = {"h": torch.zeros((b, self.channels, pad(frames)), dtype=sdt, device=dev)}
             length = frames
             for i, u in enumerate(self.upsample_scales):
                 length *= u
                 c = self._stage_channels(i)
                 for name in ("up", "r0", "r1", "sum"):
-                    ws[f"{name}{i}"] = torch.zeros((b, c, _pad4(length)), dtype=torch.float32, device=dev)
+                    ws[f"{name}{i}"] = torch.zeros((b, c, pad(length)), dtype=sdt, device=dev)
                 # value between the two convs of a residual pair: an MMA operand only -> fp16 in the
                 # fp16-operand mode, fp32 otherwise
                 tdt = torch.float16 if self.precision == "f16" else torch.float32
@@ -167,7 +174,7 @@ class HiFiGANGenerator(_GeneratorBase):
                  upsample_scales=(8, 6, 4, 2), upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
                  resblock_dilations=((1, 3, 5), (1, 3, 5), (1, 3, 5)), use_additional_convs=True, bias=True,
                  nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
-                 use_weight_norm=True, precision="f16"):
+                 use_weight_norm=True, precision="f16", activation_dtype="f32"):
         super().__init__()
         if not (use_additional_convs and bias and use_weight_norm and nonlinear_activation == "LeakyReLU"
                 and nonlinear_activation_params.get("negative_slope", 0.1) == 0.1 and out_channels == 1):
@@ -178,7 +185,7 @@ class HiFiGANGenerator(_GeneratorBase):
         lay, alias = layouts.hifigan_layout(in_channels, out_channels, channels, kernel_size, upsample_scales,
                                             upsample_kernel_sizes, resblock_kernel_sizes, resblock_dilations)
         layouts.attach(self, lay, alias)
-        self._init_engine(precision)
+        self._init_engine(precision, activation_dtype)
         if path_to_weights is not None:
             self.load_state_dict(torch.load(path_to_weights, map_location="cpu")["generator"])
 
@@ -201,7 +208,7 @@ class BigVGAN(_GeneratorBase):
 
     def __init__(self, path_to_weights, num_mels=80, upsample_initial_channel=512, upsample_rates=(8, 6, 4, 2),
                  upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
-                 resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), precision="f16"):
+                 resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), precision="f16", activation_dtype="f32"):
         super().__init__()
         self.in_channels, self.channels, self.kernel_size = num_mels, upsample_initial_channel, 7
         self.upsample_scales, self.upsample_kernel_sizes = tuple(upsample_rates), tuple(upsample_kernel_sizes)
@@ -213,7 +220,7 @@ class BigVGAN(_GeneratorBase):
         lay, alias = layouts.bigvgan_layout(num_mels, upsample_initial_channel, upsample_rates, upsample_kernel_sizes,
                                             resblock_kernel_sizes, resblock_dilation_sizes, filter_buffers=has_filters)
         layouts.attach(self, lay, alias)
-        self._init_engine(precision)
+        self._init_engine(precision, activation_dtype)
         if sd is not None:
             self.load_state_dict(sd)
 

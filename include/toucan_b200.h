@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TB200_VERSION 100
+#define TB200_VERSION 101
 
 enum {
   TB200_OK = 0,
@@ -107,7 +107,8 @@ typedef struct tb200_conv1d_params {
   /* epilogue */
   int32_t out_act;          /* TB200_OUT_*                                              */
   float out_alpha;
-  const float* residual;    /* (B, C_out, L_out) fp32 or NULL                           */
+  const void* residual;     /* (B, C_out, L_out) or NULL                                */
+  int32_t r_dtype;          /* TB200_F32 | TB200_F16                                    */
   int64_t r_bs; int32_t r_ld;
   float res_beta;
   int32_t accumulate;       /* y += ...                                                 */
