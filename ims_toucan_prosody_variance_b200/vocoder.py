@@ -107,7 +107,6 @@ class _GeneratorBase(torch.nn.Module):
                 tdt = torch.float16 if self.precision == "f16" else torch.float32
                 # row pitch a multiple of 8 elements: the lane=channel snake staging reads 16-byte groups
                 ws[f"t{i}"] = torch.zeros((b, c, _pad8(length) + 8), dtype=tdt, device=dev)
-            ws["wave"] = torch.zeros((b, 1, _pad4(length)), dtype=torch.float32, device=dev)
             self._buffers_cache[key] = ws
         return ws
 
@@ -115,7 +114,7 @@ class _GeneratorBase(torch.nn.Module):
     @torch.no_grad()
     def forward_batch(self, c, lengths=None):
         """c (B,80,F) fp32 CUDA; lengths (B) frames per utterance (int tensor) or None.
-        Returns wave (B, F*prod(scales)) fp32; samples past lengths[b]*384 are unspecified."""
+        Returns a new tensor wave (B, F*prod(scales)) fp32; samples past lengths[b]*384 are zero."""
         if self._packed is None:
             self.remove_weight_norm()
         pk = self._packed
@@ -156,8 +155,9 @@ class _GeneratorBase(torch.nn.Module):
                                                    beta=a2[1], residual=cur)
             h = total
         pa = pk.get("post_act", (None, None))
-        wave = pk["post"](h, len_t, ws["wave"], l_in_max=length, act=self.post_act, slope=0.01, alpha=pa[0], beta=pa[1],
-                          out_act=OUT_TANH)
+        # the result is a fresh tensor (the intermediates live in the cached workspace and are overwritten by the next call)
+        wave = torch.zeros((b, 1, _pad4(length)), dtype=torch.float32, device=dev)
+        pk["post"](h, len_t, wave, l_in_max=length, act=self.post_act, slope=0.01, alpha=pa[0], beta=pa[1], out_act=OUT_TANH)
         return wave[:, 0, :length]
 
     def forward(self, c, *args, **kwargs):
