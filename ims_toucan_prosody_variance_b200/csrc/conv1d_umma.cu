@@ -103,7 +103,7 @@ template <typename T>
 __device__ __forceinline__ T to_operand(float v);
 template <>
 __device__ __forceinline__ __half to_operand<__half>(float v) {
-  return __float2half_rn(clamp_f16(v));
+  return f16_sat(v);
 }
 template <>
 __device__ __forceinline__ float to_operand<float>(float v) {
@@ -118,15 +118,11 @@ struct UmmaStore {
   __device__ __forceinline__ void operator()(int g, int r, const float (&v)[ElemTraits<T>::kEpc]) const {
     T* dst = base + ((long long)g * R + r) * ElemTraits<T>::kEpc;
     if constexpr (ElemTraits<T>::kEpc == 8) {
-      __half2 h0 = __floats2half2_rn(clamp_f16(v[0]), clamp_f16(v[1]));
-      __half2 h1 = __floats2half2_rn(clamp_f16(v[2]), clamp_f16(v[3]));
-      __half2 h2 = __floats2half2_rn(clamp_f16(v[4]), clamp_f16(v[5]));
-      __half2 h3 = __floats2half2_rn(clamp_f16(v[6]), clamp_f16(v[7]));
       uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2);
-      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      u.x = f16x2_sat(v[0], v[1]);
+      u.y = f16x2_sat(v[2], v[3]);
+      u.z = f16x2_sat(v[4], v[5]);
+      u.w = f16x2_sat(v[6], v[7]);
       *reinterpret_cast<uint4*>(dst) = u;
     } else {
       *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
@@ -276,11 +272,9 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
               v[e] = valid ? apply_pointwise(xv, a.act, a.slope) : 0.f;
             }
             if (r >= 0 && r < R) {
-              const __half2 h0 = __floats2half2_rn(clamp_f16(v[0]), clamp_f16(v[1]));
-              const __half2 h1 = __floats2half2_rn(clamp_f16(v[2]), clamp_f16(v[3]));
               uint2 o;
-              o.x = *reinterpret_cast<const uint32_t*>(&h0);
-              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              o.x = f16x2_sat(v[0], v[1]);
+              o.y = f16x2_sat(v[2], v[3]);
               *reinterpret_cast<uint2*>(dst + (long long)i * E) = o;
             }
           }
@@ -301,11 +295,9 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
           }
           if (r >= 0 && r < R) {
             if constexpr (E == 8) {
-              const __half2 h0 = __floats2half2_rn(clamp_f16(v[0]), clamp_f16(v[1]));
-              const __half2 h1 = __floats2half2_rn(clamp_f16(v[2]), clamp_f16(v[3]));
               uint2 o;
-              o.x = *reinterpret_cast<const uint32_t*>(&h0);
-              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              o.x = f16x2_sat(v[0], v[1]);
+              o.y = f16x2_sat(v[2], v[3]);
               *reinterpret_cast<uint2*>(dst + (long long)i * E) = o;
             } else {
               *reinterpret_cast<float4*>(dst + (long long)i * E) =
@@ -527,6 +519,8 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float*
   __half* yh = reinterpret_cast<__half*>(a.y);
   const uint32_t y_ld = (uint32_t)a.y_ld;
   const bool relu = a.out_act == TB200_OUT_RELU;
+  const bool y_f16 = a.y_f16 != 0;
+  const float out_alpha = a.out_alpha, beta0 = ax0.beta, beta1 = ax1.beta;
   auto fetch1 = [&](int k, const EpiAux& ax, float (&r)[16]) {
     const int sl = k / nsub, sub = k - sl * nsub;
     const uint32_t n0 = (uint32_t)(nt * a.NT + (slab0 + sl * slab_step) * 16);
@@ -557,16 +551,33 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float*
     __syncwarp();
     tmem_ld_x16(tm0 + (uint32_t)(sub * a.NT + s * 16), v);
     tmem_ld_wait();
-    uint32_t yo = ybase + n0 * y_ld + (uint32_t)m;
+    // all per-item switches (ReLU, output type, row inside the utterance) are warp-uniform or hoisted out of the
+    // 16-column loops: the per-element work is 2 FFMA + address add + store
+    float val[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i, yo += y_ld) {
-      float val = fmaf(__uint_as_float(v[i]), a.out_alpha, bias[i]);
-      if (relu) val = fmaxf(val, 0.f);   // alpha * relu(x) == relu(alpha * x) for alpha >= 0 (host-checked)
-      if constexpr (NAUX >= 1) val = fmaf(ax0.beta, r0[i], val);
-      if constexpr (NAUX >= 2) val = fmaf(ax1.beta, r1[i], val);
-      if (row_ok) {
-        if (a.y_f16) yh[yo] = __float2half_rn(clamp_f16(val));
-        else yf[yo] = val;
+    for (int i = 0; i < 16; ++i) val[i] = fmaf(__uint_as_float(v[i]), out_alpha, bias[i]);
+    if (relu) {   // alpha * relu(x) == relu(alpha * x) for alpha >= 0 (host-checked)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) val[i] = fmaxf(val[i], 0.f);
+    }
+    if constexpr (NAUX >= 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) val[i] = fmaf(beta0, r0[i], val[i]);
+    }
+    if constexpr (NAUX >= 2) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) val[i] = fmaf(beta1, r1[i], val[i]);
+    }
+    if (row_ok) {
+      const uint32_t yo = ybase + n0 * y_ld + (uint32_t)m;
+      if (y_f16) {
+        __half* yp = yh + yo;
+#pragma unroll
+        for (int i = 0; i < 16; ++i, yp += y_ld) *yp = f16_sat(val[i]);
+      } else {
+        float* yp = yf + yo;
+#pragma unroll
+        for (int i = 0; i < 16; ++i, yp += y_ld) *yp = val[i];
       }
     }
   };
@@ -633,7 +644,7 @@ __device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t t
           const long long yi = ybase + (long long)co * a.y_ld + t;
           if (plain_out) {
             const float val = (__uint_as_float(v[i]) + (a.bias ? __ldg(a.bias + co) : 0.f)) * a.out_alpha;
-            if (a.y_f16) reinterpret_cast<__half*>(a.y)[yi] = __float2half_rn(clamp_f16(val));
+            if (a.y_f16) reinterpret_cast<__half*>(a.y)[yi] = f16_sat(val);
             else reinterpret_cast<float*>(a.y)[yi] = val;
           } else {
             store_y(a, yi, finish(__uint_as_float(v[i]), a, co, rbase + (long long)co * a.r_ld + t, yi));
