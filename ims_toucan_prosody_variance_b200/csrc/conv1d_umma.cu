@@ -360,6 +360,9 @@ __device__ __forceinline__ constexpr float aa_tap(int k) {
 // One (32-channel block, row segment) task.  EDGE segments (near the utterance's ends) read x with clamped indices
 // (replicate padding of the 2x up-sampler), clamp the snake output index to [0, 2 len) (replicate padding of the
 // down-sampler) and emit zeros outside [0, len); interior segments are compiled without any of these branches.
+#ifndef TB200_SNAKE_PACKED
+#define TB200_SNAKE_PACKED 1   // steady snake blocks on FFMA2 pairs (0: scalar FFMA blocks)
+#endif
 template <typename T, bool EDGE>
 __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row, int c, int t_lo, int t_beg, int t_end,
                                                 int len, T* dst) {
@@ -430,14 +433,114 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
       }
     }
   };
-  for (int base = ts; base - 6 < t_end; base += 8) {
-    loadx(base + 16, n2);
-    if (!EDGE && base - 6 >= t_beg && base + 1 < t_end) block8(std::false_type{}, base);
-    else block8(std::true_type{}, base);
+  // Steady 8-step block on packed fp32 pairs: lane half "lo" runs step n = base + j, half "hi" step n + 4 (j = 0..3),
+  // so every FIR tap is one FFMA2 over (x[n+..], x[n+4+..]) with the tap as an immediate.  Each half performs exactly
+  // the scalar block's operations in the same order (bit-identical results).  State between packed blocks:
+  //   XA[i]  = (x[base-8+i], x[base-4+i])                        i = 0..3
+  //   PS0[j] = (s0[base-11+j], s0[base-7+j]), PS1[j] likewise    j = 0..3   (s0/s1 = the two snake outputs of a pair)
+  uint64_t XA[4], PS0[4], PS1[4];
+  auto block8_packed = [&](int base) {
+    uint64_t XP[10], NA[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) NA[i] = pk2(cur[i], cur[i + 4]);
+    XP[0] = XA[2];
+    XP[1] = XA[3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      XP[2 + i] = pk2(hi2(XA[i]), cur[i]);      // (x[base-4+i], x[base+i])
+      XP[6 + i] = NA[i];
+    }
+    const uint64_t ea2 = pk2(ea, ea), ib2 = pk2(ib, ib);
+    uint64_t NS0[4], NS1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t u0 = 0ull, u1 = 0ull;              // (+0.f, +0.f)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        u0 = ffma2(XP[j + q], pk2(2.f * aa_tap(11 - 2 * q), 2.f * aa_tap(11 - 2 * q)), u0);
+        u1 = ffma2(XP[j + 1 + q], pk2(2.f * aa_tap(10 - 2 * q), 2.f * aa_tap(10 - 2 * q)), u1);
+      }
+      float a0l, a0h, a1l, a1h;
+      upk2(fmul2(u0, ea2), a0l, a0h);
+      upk2(fmul2(u1, ea2), a1l, a1h);
+      const uint64_t z0 = pk2(__sinf(a0l), __sinf(a0h)), z1 = pk2(__sinf(a1l), __sinf(a1h));
+      NS0[j] = ffma2(fmul2(ib2, z0), z0, u0);
+      NS1[j] = ffma2(fmul2(ib2, z1), z1, u1);
+    }
+    uint64_t SP0[10], SP1[10];                    // SP?[r] = (s?[base-9+r], s?[base-5+r])
+    SP0[0] = PS0[2]; SP0[1] = PS0[3];
+    SP1[0] = PS1[2]; SP1[1] = PS1[3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      SP0[2 + j] = pk2(hi2(PS0[j]), lo2(NS0[j]));
+      SP1[2 + j] = pk2(hi2(PS1[j]), lo2(NS1[j]));
+      SP0[6 + j] = NS0[j];
+      SP1[6 + j] = NS1[j];
+    }
+    T* drow = dst + (long long)(base - 6 - t_lo) * E;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t o0 = 0ull, o1 = 0ull;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        o0 = ffma2(pk2(aa_tap(2 * i), aa_tap(2 * i)), SP1[j + i], o0);
+        o1 = ffma2(pk2(aa_tap(2 * i + 1), aa_tap(2 * i + 1)), SP0[j + i + 1], o1);
+      }
+      float ol, oh;
+      upk2(fadd2(o0, o1), ol, oh);
+      if constexpr (sizeof(T) == 2) {
+        const uint32_t h = f16x2_sat(ol, oh);
+        *reinterpret_cast<unsigned short*>(drow + j * E) = (unsigned short)(h & 0xffffu);
+        *reinterpret_cast<unsigned short*>(drow + (j + 4) * E) = (unsigned short)(h >> 16);
+      } else {
+        drow[j * E] = to_operand<T>(ol);
+        drow[(j + 4) * E] = to_operand<T>(oh);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      XA[i] = NA[i];
+      PS0[i] = NS0[i];
+      PS1[i] = NS1[i];
+    }
+  };
+  auto rotate = [&]() {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       cur[i] = n1[i];
       n1[i] = n2[i];
+    }
+  };
+  int base = ts;
+  while (base - 6 < t_end) {
+    bool steady = false;
+    if constexpr (!EDGE) steady = TB200_SNAKE_PACKED && base - 6 >= t_beg && base + 1 < t_end;
+    if (steady) {
+      // scalar windows -> packed state (base % 8 == 0: xw[i] = x[base-8+i]; pair P lives in sv[2 (P & 7)], +1)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        XA[i] = pk2(xw[i], xw[i + 4]);
+        PS0[i] = pk2(sv[2 * ((5 + i) & 7)], sv[2 * ((1 + i) & 7)]);
+        PS1[i] = pk2(sv[2 * ((5 + i) & 7) + 1], sv[2 * ((1 + i) & 7) + 1]);
+      }
+      do {
+        loadx(base + 16, n2);
+        block8_packed(base);
+        rotate();
+        base += 8;
+      } while (base + 1 < t_end);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        upk2(XA[i], xw[i], xw[i + 4]);
+        upk2(PS0[i], sv[2 * ((5 + i) & 7)], sv[2 * ((1 + i) & 7)]);
+        upk2(PS1[i], sv[2 * ((5 + i) & 7) + 1], sv[2 * ((1 + i) & 7) + 1]);
+      }
+    } else {
+      loadx(base + 16, n2);
+      if (!TB200_SNAKE_PACKED && !EDGE && base - 6 >= t_beg && base + 1 < t_end) block8(std::false_type{}, base);
+      else block8(std::true_type{}, base);
+      rotate();
+      base += 8;
     }
   }
 }
@@ -448,11 +551,24 @@ __device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int
   constexpr int E = ElemTraits<T>::kEpc;
   const int R = a.R;
   const int seg_rows = (R + nseg - 1) / nseg;
+  // Interior segment boundaries sit where (t + 6) % 8 == 0 (absolute time): the first output of the segment is then
+  // the first output of a steady 8-step block and its last output the last of one, so only the tile's first and last
+  // segment run partial (checked) blocks.  Needs seg_rows >= 8 to keep the boundaries increasing.
+  auto seg_start = [&](int sgm) {
+    if (sgm <= 0) return 0;
+    if (sgm >= nseg) return R;
+    int r = sgm * seg_rows;
+    if (seg_rows >= 8) {
+      const int ph = (t_lo + r + 6) & 7;          // two's complement: correct for negative t_lo as well
+      r += ph > 4 ? 8 - ph : -ph;
+    }
+    return min(max(r, 0), R);
+  };
   const long long xb = (long long)b * a.x_bs;
   for (int task = pw; task < ncb * nseg; task += a.n_prod) {
     const int cb = task / nseg, seg = task - cb * nseg;
-    const int r_beg = seg * seg_rows;
-    const int r_end = min(R, r_beg + seg_rows);
+    const int r_beg = seg_start(seg);
+    const int r_end = seg_start(seg + 1);
     if (r_beg >= r_end) continue;
     const int cl = cb * 32 + lane;          // channel inside this staged panel
     const int c = cb0 * 32 + cl;            // absolute input channel
