@@ -89,11 +89,14 @@ struct ElemTraits<float> {
 //  4 epilogue: acc_full acquired  5 epilogue: tile drained    6 MMA: acc_empty acquired
 constexpr int kTraceTiles = 96;
 constexpr int kTraceCtas = 160;   // after the tile stamps: elapsed cycles and %smid of every CTA
+constexpr int kTraceWarps = 32;   // then (start, end) of every producer warp of CTA 0 while staging its 6th A buffer
+constexpr int kTraceLen = kTraceTiles * 8 + kTraceCtas + 2 * kTraceWarps;
 __device__ __forceinline__ void trace(const ConvArgs& a, int slot, uint32_t idx) {
   if (a.trace && blockIdx.x == 0 && idx < (uint32_t)kTraceTiles) a.trace[idx * 8 + slot] = clock64();
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -329,21 +332,31 @@ __device__ TB200_ROLE_INLINE void stage_pointwise_vec(const ConvArgs& a, int b, 
 //   out(n-6) = down-filter over pairs n-9 .. n-3.
 // A warp task = (32-channel block, row segment).  Requires every touched x index inside [0, len).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load8(const void* x, bool f16, long long idx, float (&r)[8]) {
-  if (f16) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + idx));
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f2 = __half22float2(h[i]);
-      r[2 * i] = f2.x;
-      r[2 * i + 1] = f2.y;
-    }
+// 8 consecutive inputs of one channel as loaded (fp16: 4 words, fp32: 8 words); converted where they are used, so the
+// loads can run far ahead of their first consumer and an fp16 buffer costs 4 registers
+template <bool XF16>
+struct XRaw {
+  uint32_t w[XF16 ? 4 : 8];
+};
+template <bool XF16>
+__device__ __forceinline__ float xget(const XRaw<XF16>& b, int i) {
+  if constexpr (XF16) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&b.w[i >> 1]);
+    return (i & 1) ? __high2float(h) : __low2float(h);
   } else {
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + idx));
-    const float4 p1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + idx + 4));
-    r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = p0.w;
-    r[4] = p1.x; r[5] = p1.y; r[6] = p1.z; r[7] = p1.w;
+    return __uint_as_float(b.w[i]);
+  }
+}
+template <bool XF16>
+__device__ __forceinline__ void load8(const void* x, long long idx, XRaw<XF16>& r) {
+  if constexpr (XF16) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + idx));
+    r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
+  } else {
+    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(x) + idx));
+    const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(x) + idx + 4));
+    r.w[0] = p0.x; r.w[1] = p0.y; r.w[2] = p0.z; r.w[3] = p0.w;
+    r.w[4] = p1.x; r.w[5] = p1.y; r.w[6] = p1.z; r.w[7] = p1.w;
   }
 }
 
@@ -360,30 +373,49 @@ __device__ __forceinline__ constexpr float aa_tap(int k) {
 // One (32-channel block, row segment) task.  EDGE segments (near the utterance's ends) read x with clamped indices
 // (replicate padding of the 2x up-sampler), clamp the snake output index to [0, 2 len) (replicate padding of the
 // down-sampler) and emit zeros outside [0, len); interior segments are compiled without any of these branches.
+#ifndef TB200_SNAKE_PFL1
+#define TB200_SNAKE_PFL1 0   // steady blocks: L1 prefetch distance in time steps (0 = off)
+#endif
 #ifndef TB200_SNAKE_PACKED
 #define TB200_SNAKE_PACKED 1   // steady snake blocks on FFMA2 pairs (0: scalar FFMA blocks)
 #endif
-template <typename T, bool EDGE>
+template <typename T, bool EDGE, bool XF16>
 __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row, int c, int t_lo, int t_beg, int t_end,
                                                 int len, T* dst) {
   constexpr int E = ElemTraits<T>::kEpc;
   const int ts = (t_beg - 9) & ~7;        // first ingested step, 16-byte aligned
   const float ea = __expf(__ldg(a.alpha + c));
   const float ib = 1.0f / (__expf(__ldg(a.beta + c)) + 1e-9f);
-  float xw[8], sv[16], cur[8], n1[8], n2[8];
-  auto loadx = [&](int base, float (&r)[8]) {
+  float xw[8], sv[16];
+  XRaw<XF16> cur, n1, n2;
+  auto loadx = [&](int base, XRaw<XF16>& r) {
     if (!EDGE || (base >= 0 && base + 8 <= len)) {
-      load8(a.x, a.x_f16, row + base, r);
+      load8<XF16>(a.x, row + base, r);
     } else {
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = load_x(a.x, a.x_f16, row + min(max(base + i, 0), len - 1));
+      for (int i = 0; i < 8; ++i) v[i] = load_x(a.x, XF16, row + min(max(base + i, 0), len - 1));
+      if constexpr (XF16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);   // exact: the values are fp16
+          r.w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.w[i] = __float_as_uint(v[i]);
+      }
     }
   };
   float s_first = 0.f, s_last = 0.f;
   if (EDGE && t_beg < 3) {                // s[0]: what the down-sampler sees left of the utterance
-    float u = 0.f;
+    float ue = 0.f, uo = 0.f;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) u = fmaf(load_x(a.x, a.x_f16, row + min(max(q - 3, 0), len - 1)), 2.f * aa_tap(11 - 2 * q), u);
+    for (int q = 0; q < 6; q += 2) {
+      ue = fmaf(load_x(a.x, XF16, row + min(max(q - 3, 0), len - 1)), 2.f * aa_tap(11 - 2 * q), ue);
+      uo = fmaf(load_x(a.x, XF16, row + min(max(q - 2, 0), len - 1)), 2.f * aa_tap(9 - 2 * q), uo);
+    }
+    const float u = ue + uo;
     const float z = __sinf(u * ea);
     s_first = fmaf(ib * z, z, u);
   }
@@ -400,14 +432,18 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = base + j;
-      xw[j] = cur[j];
+      xw[j] = xget(cur, j);
       if (!CHECK || n >= t_beg) {  // pair(n-3) is first needed by out(t_beg)
-        float u0 = 0.f, u1 = 0.f;
+        // even and odd taps in separate chains (the order the packed steady block needs; see block8_packed)
+        float u0e = 0.f, u0o = 0.f, u1e = 0.f, u1o = 0.f;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          u0 = fmaf(xw[(j + 2 + q) & 7], 2.f * aa_tap(11 - 2 * q), u0);   // x[n-6+q]; the x2 of the up-sampler is exact
-          u1 = fmaf(xw[(j + 3 + q) & 7], 2.f * aa_tap(10 - 2 * q), u1);   // x[n-5+q]
+        for (int q = 0; q < 6; q += 2) {
+          u0e = fmaf(xw[(j + 2 + q) & 7], 2.f * aa_tap(11 - 2 * q), u0e);   // x[n-6+q]; the x2 of the up-sampler is exact
+          u0o = fmaf(xw[(j + 3 + q) & 7], 2.f * aa_tap(9 - 2 * q), u0o);    // x[n-6+(q+1)]
+          u1e = fmaf(xw[(j + 3 + q) & 7], 2.f * aa_tap(10 - 2 * q), u1e);   // x[n-5+q]
+          u1o = fmaf(xw[(j + 4 + q) & 7], 2.f * aa_tap(8 - 2 * q), u1o);    // x[n-5+(q+1)]
         }
+        const float u0 = u0e + u0o, u1 = u1o + u1e;
         const float z0 = __sinf(u0 * ea), z1 = __sinf(u1 * ea);
         float s0 = fmaf(ib * z0, z0, u0), s1 = fmaf(ib * z1, z1, u1);
         if constexpr (EDGE) {
@@ -421,95 +457,114 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
       }
       const int t = n - 6;
       if (!CHECK || (t >= t_beg && t < t_end)) {
-        float o0 = 0.f, o1 = 0.f;
+        // out[t] = sum_i tap[2i] s1[t-3+i] + tap[2i+1] s0[t-2+i]; pair P lives in sv[2 (P & 7)] (s0), +1 (s1).
+        // chain A: s1 terms i = 0,2,4 then s0 terms i = 1,3,5; chain B: s1 terms i = 1,3,5 then s0 terms i = 0,2,4
+        float oa = 0.f, ob = 0.f;
 #pragma unroll
-        for (int k = 0; k < 12; k += 2) {  // s[2t-5+k] = pair (n-9+(k+1)/2), element (k+1)&1
-          o0 = fmaf(aa_tap(k), sv[2 * ((j + 7 + ((k + 1) >> 1)) & 7) + ((k + 1) & 1)], o0);
-          o1 = fmaf(aa_tap(k + 1), sv[2 * ((j + 7 + ((k + 2) >> 1)) & 7) + ((k + 2) & 1)], o1);
+        for (int i = 0; i < 6; i += 2) {
+          oa = fmaf(aa_tap(2 * i), sv[2 * ((j + 7 + i) & 7) + 1], oa);
+          ob = fmaf(aa_tap(2 * i + 2), sv[2 * ((j + 8 + i) & 7) + 1], ob);
         }
-        float o = o0 + o1;
+#pragma unroll
+        for (int i = 0; i < 6; i += 2) {
+          oa = fmaf(aa_tap(2 * i + 3), sv[2 * ((j + 9 + i) & 7)], oa);
+          ob = fmaf(aa_tap(2 * i + 1), sv[2 * ((j + 8 + i) & 7)], ob);
+        }
+        float o = oa + ob;
         if (EDGE && (t < 0 || t >= len)) o = 0.f;
         drow[j * E] = to_operand<T>(o);
       }
     }
   };
-  // Steady 8-step block on packed fp32 pairs: lane half "lo" runs step n = base + j, half "hi" step n + 4 (j = 0..3),
-  // so every FIR tap is one FFMA2 over (x[n+..], x[n+4+..]) with the tap as an immediate.  Each half performs exactly
-  // the scalar block's operations in the same order (bit-identical results).  State between packed blocks:
-  //   XA[i]  = (x[base-8+i], x[base-4+i])                        i = 0..3
-  //   PS0[j] = (s0[base-11+j], s0[base-7+j]), PS1[j] likewise    j = 0..3   (s0/s1 = the two snake outputs of a pair)
-  uint64_t XA[4], PS0[4], PS1[4];
-  auto block8_packed = [&](int base) {
-    uint64_t XP[10], NA[4];
+  // Steady 8-step block on packed fp32 pairs (FFMA2: two fp32 lanes per issued instruction, taps as immediates).
+  // A pair holds two ADJACENT time steps, XP(m) = (x[m], x[m+1]) with m even -- the layout the 16-byte loads deliver --
+  // and every FIR is split by tap parity so that each product reads an aligned pair:
+  //   u0[p] = sum_q A0[q] x[p-3+q],  u1[p] = sum_q A1[q] x[p-2+q]          (pair p of the 2x up-sampled signal)
+  //   for odd p:  E0(p) = sum_{q even} A0[q] XP(p-3+q)  -> lanes (u0[p], u0[p+1]) partial
+  //               O0(p) = sum_{q odd}  A0[q] XP(p-2+q)  -> lanes (u0[p+1], u0[p+2]) partial
+  //               (u0[p], u0[p+1]) = (lo E0(p) + hi O0(p-2), hi E0(p) + lo O0(p));  u1 likewise with the parities swapped
+  //   out[t] = sum_i tap[2i] s1[t-3+i] + tap[2i+1] s0[t-2+i];  for even t:
+  //               A(t) = s1 terms i even + s0 terms i odd -> lanes (out[t], out[t+1]) partial
+  //               B(t) = s1 terms i odd + s0 terms i even -> lanes (out[t+1], out[t+2]) partial
+  // Every element sees exactly the scalar block's operations in the same order (bit-identical results).
+  // State between packed blocks (base % 8 == 0):
+  //   XH[m] = XP(base-6+2m) m<3;  OH0/OH1 = O0/O1(base-5);  S1H[m] = S1P(base-9+2m), S0H[m] = S0P(base-9+2m) m<3;  BH = B(base-8)
+  uint64_t XH[3], OH0, OH1, S1H[3], S0H[3], BH;
+  uint64_t S1Q[7], S0Q[7];                        // S?Q[m] = S?P(base-9+2m) of the block in flight
+  auto block8_up = [&](const XRaw<XF16>& xb) {
+    uint64_t XQ[7];                               // XQ[m] = XP(base-6+2m)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) NA[i] = pk2(cur[i], cur[i + 4]);
-    XP[0] = XA[2];
-    XP[1] = XA[3];
+    for (int m = 0; m < 3; ++m) XQ[m] = XH[m];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      XP[2 + i] = pk2(hi2(XA[i]), cur[i]);      // (x[base-4+i], x[base+i])
-      XP[6 + i] = NA[i];
+    for (int k = 0; k < 4; ++k) XQ[3 + k] = pk2(xget(xb, 2 * k), xget(xb, 2 * k + 1));
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      S1Q[m] = S1H[m];
+      S0Q[m] = S0H[m];
     }
-    const uint64_t ea2 = pk2(ea, ea), ib2 = pk2(ib, ib);
-    uint64_t NS0[4], NS1[4];
+#define TAP2(v) pk2((v), (v))
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint64_t u0 = 0ull, u1 = 0ull;              // (+0.f, +0.f)
+    for (int k = 0; k < 4; ++k) {                 // pairs p = base-3+2k, p+1
+      uint64_t e0 = 0ull, o0 = 0ull, e1 = 0ull, o1 = 0ull;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        u0 = ffma2(XP[j + q], pk2(2.f * aa_tap(11 - 2 * q), 2.f * aa_tap(11 - 2 * q)), u0);
-        u1 = ffma2(XP[j + 1 + q], pk2(2.f * aa_tap(10 - 2 * q), 2.f * aa_tap(10 - 2 * q)), u1);
+      for (int r = 0; r < 3; ++r) {
+        e0 = ffma2(XQ[k + r], TAP2(2.f * aa_tap(11 - 4 * r)), e0);          // A0[2r]   XP(p-3+2r)
+        o0 = ffma2(XQ[k + 1 + r], TAP2(2.f * aa_tap(9 - 4 * r)), o0);       // A0[2r+1] XP(p-1+2r)
+        e1 = ffma2(XQ[k + 1 + r], TAP2(2.f * aa_tap(8 - 4 * r)), e1);       // A1[2r+1] XP(p-1+2r)
+        o1 = ffma2(XQ[k + 1 + r], TAP2(2.f * aa_tap(10 - 4 * r)), o1);      // A1[2r]   XP(p-1+2r)
       }
+      const uint64_t u0 = pk2(lo2(e0) + hi2(OH0), hi2(e0) + lo2(o0));
+      const uint64_t u1 = pk2(hi2(OH1) + lo2(e1), lo2(o1) + hi2(e1));
+      OH0 = o0;
+      OH1 = o1;
       float a0l, a0h, a1l, a1h;
-      upk2(fmul2(u0, ea2), a0l, a0h);
-      upk2(fmul2(u1, ea2), a1l, a1h);
+      upk2(fmul2(u0, pk2(ea, ea)), a0l, a0h);
+      upk2(fmul2(u1, pk2(ea, ea)), a1l, a1h);
       const uint64_t z0 = pk2(__sinf(a0l), __sinf(a0h)), z1 = pk2(__sinf(a1l), __sinf(a1h));
-      NS0[j] = ffma2(fmul2(ib2, z0), z0, u0);
-      NS1[j] = ffma2(fmul2(ib2, z1), z1, u1);
+      S0Q[3 + k] = ffma2(fmul2(pk2(ib, ib), z0), z0, u0);
+      S1Q[3 + k] = ffma2(fmul2(pk2(ib, ib), z1), z1, u1);
     }
-    uint64_t SP0[10], SP1[10];                    // SP?[r] = (s?[base-9+r], s?[base-5+r])
-    SP0[0] = PS0[2]; SP0[1] = PS0[3];
-    SP1[0] = PS1[2]; SP1[1] = PS1[3];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      SP0[2 + j] = pk2(hi2(PS0[j]), lo2(NS0[j]));
-      SP1[2 + j] = pk2(hi2(PS1[j]), lo2(NS1[j]));
-      SP0[6 + j] = NS0[j];
-      SP1[6 + j] = NS1[j];
-    }
-    T* drow = dst + (long long)(base - 6 - t_lo) * E;
+    for (int m = 0; m < 3; ++m) XH[m] = XQ[4 + m];
+  };
+  T* drow_run = dst;                              // row of out[base - 6] of the packed block in flight
+  auto block8_down = [&]() {
+    T* drow = drow_run;
+    drow_run += 8 * E;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint64_t o0 = 0ull, o1 = 0ull;
+    for (int k = 0; k < 4; ++k) {                 // outputs t = base-6+2k, t+1
+      uint64_t oa = 0ull, ob = 0ull;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        o0 = ffma2(pk2(aa_tap(2 * i), aa_tap(2 * i)), SP1[j + i], o0);
-        o1 = ffma2(pk2(aa_tap(2 * i + 1), aa_tap(2 * i + 1)), SP0[j + i + 1], o1);
+      for (int r = 0; r < 3; ++r) {
+        oa = ffma2(TAP2(aa_tap(4 * r)), S1Q[k + r], oa);                     // tap[2i] s1, i = 2r:   S1P(t-3+2r)
+        ob = ffma2(TAP2(aa_tap(4 * r + 2)), S1Q[k + 1 + r], ob);             // tap[2i] s1, i = 2r+1: S1P(t-1+2r)
       }
-      float ol, oh;
-      upk2(fadd2(o0, o1), ol, oh);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        oa = ffma2(TAP2(aa_tap(4 * r + 3)), S0Q[k + 1 + r], oa);             // tap[2i+1] s0, i = 2r+1: S0P(t-1+2r)
+        ob = ffma2(TAP2(aa_tap(4 * r + 1)), S0Q[k + 1 + r], ob);             // tap[2i+1] s0, i = 2r:   S0P(t-1+2r)
+      }
+      const float ol = lo2(oa) + hi2(BH), oh = hi2(oa) + lo2(ob);
+      BH = ob;
       if constexpr (sizeof(T) == 2) {
         const uint32_t h = f16x2_sat(ol, oh);
-        *reinterpret_cast<unsigned short*>(drow + j * E) = (unsigned short)(h & 0xffffu);
-        *reinterpret_cast<unsigned short*>(drow + (j + 4) * E) = (unsigned short)(h >> 16);
+        *reinterpret_cast<unsigned short*>(drow + (2 * k) * E) = (unsigned short)(h & 0xffffu);
+        *reinterpret_cast<unsigned short*>(drow + (2 * k + 1) * E) = (unsigned short)(h >> 16);
       } else {
-        drow[j * E] = to_operand<T>(ol);
-        drow[(j + 4) * E] = to_operand<T>(oh);
+        drow[(2 * k) * E] = to_operand<T>(ol);
+        drow[(2 * k + 1) * E] = to_operand<T>(oh);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      XA[i] = NA[i];
-      PS0[i] = NS0[i];
-      PS1[i] = NS1[i];
+    for (int m = 0; m < 3; ++m) {
+      S1H[m] = S1Q[4 + m];
+      S0H[m] = S0Q[4 + m];
     }
   };
+#undef TAP2
   auto rotate = [&]() {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      cur[i] = n1[i];
-      n1[i] = n2[i];
-    }
+    cur = n1;
+    n1 = n2;
   };
   int base = ts;
   while (base - 6 < t_end) {
@@ -518,22 +573,61 @@ __device__ __forceinline__ void aa_channel_task(const ConvArgs& a, long long row
     if (steady) {
       // scalar windows -> packed state (base % 8 == 0: xw[i] = x[base-8+i]; pair P lives in sv[2 (P & 7)], +1)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        XA[i] = pk2(xw[i], xw[i + 4]);
-        PS0[i] = pk2(sv[2 * ((5 + i) & 7)], sv[2 * ((1 + i) & 7)]);
-        PS1[i] = pk2(sv[2 * ((5 + i) & 7) + 1], sv[2 * ((1 + i) & 7) + 1]);
+      for (int m = 0; m < 3; ++m) {
+        XH[m] = pk2(xw[2 + 2 * m], xw[3 + 2 * m]);
+        S0H[m] = pk2(sv[2 * ((7 + 2 * m) & 7)], sv[2 * ((2 * m) & 7)]);
+        S1H[m] = pk2(sv[2 * ((7 + 2 * m) & 7) + 1], sv[2 * ((2 * m) & 7) + 1]);
       }
-      do {
-        loadx(base + 16, n2);
-        block8_packed(base);
-        rotate();
-        base += 8;
-      } while (base + 1 < t_end);
+      {
+        float h0 = 0.f, h1 = 0.f, hb = 0.f;     // the halves of O0/O1(base-5) and B(base-8) that reach into this block
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        upk2(XA[i], xw[i], xw[i + 4]);
-        upk2(PS0[i], sv[2 * ((5 + i) & 7)], sv[2 * ((1 + i) & 7)]);
-        upk2(PS1[i], sv[2 * ((5 + i) & 7) + 1], sv[2 * ((1 + i) & 7) + 1]);
+        for (int r = 0; r < 3; ++r) {
+          h0 = fmaf(xw[3 + 2 * r], 2.f * aa_tap(9 - 4 * r), h0);            // u0[base-3]: odd taps, x[base-5+2r]
+          h1 = fmaf(xw[3 + 2 * r], 2.f * aa_tap(10 - 4 * r), h1);           // u1[base-3]: even taps, x[base-5+2r]
+          hb = fmaf(aa_tap(4 * r + 2), sv[2 * ((2 * r) & 7) + 1], hb);      // out[base-6]: s1[base-8+2r]
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) hb = fmaf(aa_tap(4 * r + 1), sv[2 * ((2 * r) & 7)], hb);   // s0[base-8+2r]
+        OH0 = pk2(0.f, h0);
+        OH1 = pk2(0.f, h1);
+        BH = pk2(0.f, hb);
+      }
+      // Two blocks per trip on alternating load buffers: no register rotation, the packed state of one block is
+      // produced in place for the next; a buffer is reloaded (two blocks ahead) as soon as the up-sampler has consumed it.
+      drow_run = dst + (long long)(base - 6 - t_lo) * E;
+      const char* xrow = reinterpret_cast<const char*>(a.x) + row * (XF16 ? 2 : 4);
+      for (;;) {
+        if (TB200_SNAKE_PFL1 > 0) {
+          // register look-ahead is short (ptxas sinks the loads to free registers): pull the sectors of the next
+          // blocks into L1 instead, which costs no registers; clamped to the utterance
+          const int tp = min(base + TB200_SNAKE_PFL1, len - 16);   // the 16 steps of one trip (two blocks)
+          prefetch_l1(xrow + (long long)tp * (XF16 ? 2 : 4));
+          if (!XF16) prefetch_l1(xrow + (long long)(tp + 8) * 4);
+          prefetch_l1(xrow + (long long)(tp + 16) * (XF16 ? 2 : 4) - 1);
+        }
+        block8_up(cur);
+        if (base + 9 >= t_end) {            // last steady block: leave (cur, n1) = (x[base+8..], x[base+16..])
+          cur = n1;
+          loadx(base + 16, n1);
+          block8_down();
+          base += 8;
+          break;
+        }
+        loadx(base + 16, cur);
+        block8_down();
+        base += 8;
+        block8_up(n1);
+        loadx(base + 16, n1);
+        block8_down();
+        base += 8;
+        if (base + 1 >= t_end) break;
+      }
+      // packed state -> scalar windows (x[base-6 .. base-1], pairs base-9 .. base-4; older entries are never read again)
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        upk2(XH[m], xw[2 + 2 * m], xw[3 + 2 * m]);
+        upk2(S0H[m], sv[2 * ((7 + 2 * m) & 7)], sv[2 * ((2 * m) & 7)]);
+        upk2(S1H[m], sv[2 * ((7 + 2 * m) & 7) + 1], sv[2 * ((2 * m) & 7) + 1]);
       }
     } else {
       loadx(base + 16, n2);
@@ -580,8 +674,13 @@ __device__ TB200_ROLE_INLINE void stage_aa_channel(const ConvArgs& a, int b, int
     }
     const long long row = xb + (long long)c * a.x_ld;
     const bool edge = (((t_beg - 9) & ~7) < 0) || (t_end + 32 > len);   // warp-uniform
-    if (edge) aa_channel_task<T, true>(a, row, c, t_lo, t_beg, t_end, len, dst);
-    else aa_channel_task<T, false>(a, row, c, t_lo, t_beg, t_end, len, dst);
+    if (a.x_f16) {
+      if (edge) aa_channel_task<T, true, true>(a, row, c, t_lo, t_beg, t_end, len, dst);
+      else aa_channel_task<T, false, true>(a, row, c, t_lo, t_beg, t_end, len, dst);
+    } else {
+      if (edge) aa_channel_task<T, true, false>(a, row, c, t_lo, t_beg, t_end, len, dst);
+      else aa_channel_task<T, false, false>(a, row, c, t_lo, t_beg, t_end, len, dst);
+    }
   }
 }
 
@@ -864,6 +963,8 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
           const int buf = ai % a.a_bufs;
           mbar_wait(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
           if (threadIdx.x == 0) trace(a, 0, ai);
+          const bool trace_warp = a.trace && blockIdx.x == 0 && ai == 5 && lane == 0;
+          if (trace_warp) a.trace[kTraceTiles * 8 + kTraceCtas + 2 * warp] = clock64();
           T* smA = reinterpret_cast<T*>(smem + lay.a_off + buf * a.a_bytes);
           const int g0 = pn * groups_per_panel;
           if constexpr (SNAKE) {
@@ -895,6 +996,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
             stage_pointwise_mlp<T>(a, b, t_lo, g0, groups_per_panel, len, smA, warp, lane);
            }
           }
+          if (trace_warp) a.trace[kTraceTiles * 8 + kTraceCtas + 2 * warp + 1] = clock64();
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, %0;" ::"r"(a.n_prod * 32) : "memory");
           if (threadIdx.x == 0) {
@@ -1233,8 +1335,8 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
                    : Roles<false>::kWorkers - ((a.residual || a.accumulate || !a.epi_fast) ? 8 : 4);
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
-    if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long)));
-    TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, (kTraceTiles * 8 + kTraceCtas) * sizeof(long long), stream));
+    if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceLen * sizeof(long long)));
+    TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), stream));
     a.trace = g_trace;
   }
   a.l2_prefetch = 0;  // measured: next-tile L2 prefetch doubles DRAM reads (lines evicted before use) -- kept as a knob
@@ -1269,7 +1371,7 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
 
 int conv_trace_read(long long* host_out, int n) {
   if (!g_trace) return fail(TB200_E_BADARG, "trace: TB200_TRACE was not set");
-  TB200_CUDA_CHECK(cudaMemcpy(host_out, g_trace, sizeof(long long) * (n < kTraceTiles * 8 + kTraceCtas ? n : kTraceTiles * 8 + kTraceCtas), cudaMemcpyDeviceToHost));
+  TB200_CUDA_CHECK(cudaMemcpy(host_out, g_trace, sizeof(long long) * (n < kTraceLen ? n : kTraceLen), cudaMemcpyDeviceToHost));
   return 0;
 }
 

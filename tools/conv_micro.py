@@ -11,13 +11,14 @@ from ims_toucan_prosody_variance_b200 import ops  # noqa: E402
 cin, cout, k, dil, up, L, B, act = (int(v) for v in sys.argv[1:9])
 prec = sys.argv[9] if len(sys.argv) > 9 else "f16"
 reps = int(sys.argv[10]) if len(sys.argv) > 10 else 5
+use_res = not (len(sys.argv) > 11 and sys.argv[11] == "nores")
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 w = torch.randn((cin, cout, 2 * up) if up else (cout, cin, k), generator=g) * 0.05
 layer = ops.ConvLayer(w.to(dev), torch.zeros(cout, device=dev), dilation=dil, padding=(k - 1) // 2 * dil,
                       transposed_stride=up, precision=prec)
 x = torch.randn(B, cin, L, device=dev)
-res = torch.randn(B, cout, L * (up or 1), device=dev)
+res = torch.randn(B, cout, L * (up or 1), device=dev) if use_res else None
 y = torch.zeros(B, cout, L * (up or 1), device=dev)
 alpha = torch.zeros(cin, device=dev)
 beta = torch.zeros(cin, device=dev)
@@ -40,10 +41,13 @@ if os.environ.get("TB200_TRACE"):
     import ctypes
 
     from ims_toucan_prosody_variance_b200 import _lib
-    buf = (ctypes.c_int64 * (96 * 8 + 160))()
-    _lib.check(_lib.load().tb200_debug_trace_read(ctypes.cast(buf, ctypes.c_void_p), 96 * 8 + 160), "trace")
+    buf = (ctypes.c_int64 * (96 * 8 + 160 + 64))()
+    _lib.check(_lib.load().tb200_debug_trace_read(ctypes.cast(buf, ctypes.c_void_p), 96 * 8 + 160 + 64), "trace")
     t = torch.tensor(list(buf)[:96 * 8], dtype=torch.int64).reshape(96, 8)
-    per_cta = [(v & ((1 << 48) - 1), v >> 48) for v in list(buf)[96 * 8:] if v]
+    per_cta = [(v & ((1 << 48) - 1), v >> 48) for v in list(buf)[96 * 8:96 * 8 + 160] if v]
+    pw = list(buf)[96 * 8 + 160:]
+    w0 = min(v for v in pw[0::2] if v)
+    print("producer warps, 6th buffer (start, end, busy) cycles:", [(pw[2 * i] - w0, pw[2 * i + 1] - w0, pw[2 * i + 1] - pw[2 * i]) for i in range(32) if pw[2 * i]])
     cyc = sorted(c for c, _ in per_cta)
     print(f"per-CTA elapsed cycles over {len(cyc)} CTAs: min {cyc[0]} median {cyc[len(cyc) // 2]} max {cyc[-1]}")
     print("slowest CTAs (cycles, smid):", sorted(per_cta, reverse=True)[:6], " fastest:", sorted(per_cta)[:4])
