@@ -825,6 +825,80 @@ __device__ TB200_ROLE_INLINE void epilogue_plain(const ConvArgs& a, const float*
   }
 }
 
+// Transposed conv with nothing but bias and scale behind it (every up-sampler of the vocoders).  Column n = co*UP + phase
+// of input row m lands at t = m*UP - UP/2 + phase.  UP is a template parameter, so channel and phase of each of the
+// 16 columns of a slab are compile-time (16 % UP == 0) or uniform arithmetic (UP == 6); bias*alpha per column comes from
+// the shared-memory cache.  When UP/2 is even, phases (p, p+1) with p even are an aligned pair of one lane: 8-byte
+// (fp32) / 4-byte (fp16) stores (PAIR, host-checked alignment of y).
+template <int UP, bool PAIR>
+__device__ TB200_ROLE_INLINE void epilogue_up(const ConvArgs& a, const float* bias_s, uint32_t tm0, int nsub, int slabs,
+                                              int slab0, int slab_step, int nt, int m_base, int len_out, uint32_t ybase) {
+  float* yf = reinterpret_cast<float*>(a.y);
+  __half* yh = reinterpret_cast<__half*>(a.y);
+  const uint32_t y_ld = (uint32_t)a.y_ld;
+  const bool y_f16 = a.y_f16 != 0;
+  const float out_alpha = a.out_alpha;
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int t_first = (m_base + sub * kTileM) * UP - UP / 2;
+    for (int s = slab0; s < slabs; s += slab_step) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld_x16(tm0 + (uint32_t)(sub * a.NT + s * 16), v);
+      const uint32_t n0 = (uint32_t)(nt * a.NT + s * 16);
+      float val[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + 4 * i);
+        val[4 * i] = b4.x; val[4 * i + 1] = b4.y; val[4 * i + 2] = b4.z; val[4 * i + 3] = b4.w;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) val[i] = fmaf(__uint_as_float(v[i]), out_alpha, val[i]);
+      if constexpr (16 % UP == 0) {
+        const uint32_t co0 = n0 / UP;
+#pragma unroll
+        for (int g = 0; g < 16 / UP; ++g) {
+          const uint32_t rowoff = ybase + (co0 + g) * y_ld;
+          if constexpr (PAIR && (UP / 2) % 2 == 0) {
+#pragma unroll
+            for (int ph = 0; ph < UP; ph += 2) {
+              const int t = t_first + ph;                  // even; len_out = len*UP is even: t < len_out covers t + 1
+              if (t >= 0 && t < len_out) {
+                if (y_f16) *reinterpret_cast<uint32_t*>(yh + rowoff + t) = f16x2_sat(val[g * UP + ph], val[g * UP + ph + 1]);
+                else *reinterpret_cast<float2*>(yf + rowoff + t) = make_float2(val[g * UP + ph], val[g * UP + ph + 1]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ph = 0; ph < UP; ++ph) {
+              const int t = t_first + ph;
+              if (t >= 0 && t < len_out) {
+                if (y_f16) yh[rowoff + t] = f16_sat(val[g * UP + ph]);
+                else yf[rowoff + t] = val[g * UP + ph];
+              }
+            }
+          }
+        }
+      } else {
+        uint32_t co = n0 / UP;
+        int ph = (int)(n0 - co * UP);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int t = t_first + ph;
+          if (t >= 0 && t < len_out) {
+            if (y_f16) yh[ybase + co * y_ld + t] = f16_sat(val[i]);
+            else yf[ybase + co * y_ld + t] = val[i];
+          }
+          if (++ph == UP) {
+            ph = 0;
+            ++co;
+          }
+        }
+      }
+    }
+  }
+}
+
 // every other combination (transposed conv scatter, tanh / relu outputs)
 __device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t tm0, int nsub, int slabs, int slab0,
                                                    int slab_step, int nt, int m_base, int len_out, long long ybase,
@@ -919,6 +993,8 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
   float* bias_s = reinterpret_cast<float*>(smem + lay.bias_off);
   if (a.epi_fast)
     for (int i = threadIdx.x; i < a.N_total; i += blockDim.x) bias_s[i] = a.bias ? __ldg(a.bias + i) * a.out_alpha : 0.f;
+  else if (a.epi_up)
+    for (int i = threadIdx.x; i < a.N_total; i += blockDim.x) bias_s[i] = a.bias ? __ldg(a.bias + i / a.up) * a.out_alpha : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1163,7 +1239,21 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         if (mode == 2) epilogue_plain<2, TB200_SNAKE_EPI_BATCH>(a, bias_s, axr, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
         else if (mode == 1) epilogue_plain<1, SNAKE ? TB200_SNAKE_EPI_BATCH : 2>(a, bias_s, a.residual ? axr : axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
         else if (mode == 0) epilogue_plain<0, 2>(a, bias_s, axy, axy, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
-        else epilogue_generic(a, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, ybase, rbase);
+        else if (a.epi_up) {
+          const bool pair = a.epi_up == 2;
+          switch (a.up) {
+            case 2: epilogue_up<2, false>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase); break;
+            case 4:
+              if (pair) epilogue_up<4, true>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+              else epilogue_up<4, false>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+              break;
+            case 6: epilogue_up<6, false>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase); break;
+            default:
+              if (pair) epilogue_up<8, true>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+              else epilogue_up<8, false>(a, bias_s, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, (uint32_t)ybase);
+              break;
+          }
+        } else epilogue_generic(a, tm0, nsub, slabs, slab0, slab_step, nt, m_base, len_out, ybase, rbase);
         tc_fence_before();
         __syncwarp();
         if (ew == 0 && lane == 0) trace(a, 5, ac);
@@ -1326,13 +1416,23 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
                  a.N_total % 16 == 0 && a.N_total <= kBiasCache &&
                  y_ext < lim && r_ext < lim && a.y_bs >= 0 && a.r_bs >= 0;
   }
+  // plain transposed epilogue preconditions (see epilogue_up)
+  {
+    const long long lim = 1LL << 31;
+    const bool ok = (a.up == 2 || a.up == 4 || a.up == 6 || a.up == 8) && !a.residual && !a.accumulate &&
+                    a.out_act == TB200_OUT_NONE && a.N_total % 16 == 0 && a.N_total <= kBiasCache &&
+                    (long long)a.B * a.y_bs < lim && a.y_bs >= 0;
+    const int pair_align = a.y_f16 ? 4 : 8;
+    const bool pair = a.y_ld % 2 == 0 && a.y_bs % 2 == 0 && (reinterpret_cast<uintptr_t>(a.y) % pair_align) == 0;
+    a.epi_up = ok ? (pair ? 2 : 1) : 0;
+  }
   // warp split: the anti-aliased snake staging is the SIMT-heavy side (10 producers + 4 epilogue warps),
   // otherwise the epilogue is (6 + 8)
   // snake: 14 producers + 8 epilogue warps (18 + 4 measured slower even for store-only epilogues); pointwise: 6 + 8
   // pointwise: 6 + 8 when the epilogue fetches auxiliary rows, 10 + 4 when it only stores (staging is then the long
   // pole: measured 30 K vs 8 K cycles per tile)
   a.n_prod = snake ? Roles<true>::kWorkers - 8
-                   : Roles<false>::kWorkers - ((a.residual || a.accumulate || !a.epi_fast) ? 8 : 4);
+                   : Roles<false>::kWorkers - ((a.residual || a.accumulate || !(a.epi_fast || a.epi_up)) ? 8 : 4);
   a.trace = nullptr;
   if (getenv("TB200_TRACE")) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceLen * sizeof(long long)));

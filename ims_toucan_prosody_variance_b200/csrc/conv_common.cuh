@@ -48,6 +48,7 @@ struct ConvArgs {
   int aa_fast;            // lane=channel snake staging allowed (alignment / channel-count preconditions)
   int pw_vec;             // vectorised pointwise staging allowed (alignment preconditions)
   int epi_fast;           // plain epilogue allowed (see epilogue_plain)
+  int epi_up;             // plain transposed-conv epilogue allowed (see epilogue_up): 1 scalar stores, 2 aligned pairs
   int l2_prefetch;        // next-tile L2 prefetch (tuning knob, off by default)
   long long* trace;       // per-tile clock64() stamps of CTA 0 (TB200_TRACE debugging aid) or nullptr
   int n_prod;             // producer warps (the other worker warps run the epilogue)
