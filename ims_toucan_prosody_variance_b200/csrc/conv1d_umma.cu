@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         if (!restage_per_nt && nt > 0) break;
         for (int pn = 0; pn < a.n_panels; ++pn, ++ai) {
           const int buf = ai % a.a_bufs;
-          mbar_wait(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
+          mbar_wait_relaxed(a_empty + buf, ((ai / a.a_bufs) & 1) ^ 1);
           if (threadIdx.x == 0) trace(a, 0, ai);
           const bool trace_warp = a.trace && blockIdx.x == 0 && ai == 5 && lane == 0;
           if (trace_warp) a.trace[kTraceTiles * 8 + kTraceCtas + 2 * warp] = clock64();
@@ -1228,7 +1228,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
       }
       for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
         const int abuf = ac % a.acc_bufs;
-        mbar_wait(acc_full + abuf, (ac / a.acc_bufs) & 1);
+        mbar_wait_relaxed(acc_full + abuf, (ac / a.acc_bufs) & 1);
         if (ew == 0 && lane == 0) trace(a, 4, ac);
         tc_fence_after();
         const int slabs = a.NT / 16;
@@ -1364,6 +1364,30 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
           c.tiles_per_utt = (rows_max + S * kTileM - 1) / (S * kTileM);
           c.total_tiles = c.tiles_per_utt * c.B;
           if (pass == 0) {
+            // Snake prologue, tall tile with ONE staging buffer (weights resident): staging and MMA issue alternate.
+            // When the MMAs are a large part of a tile (many taps), stream the weights through a small ring instead
+            // and double-buffer the staging -- estimated from the in-kernel traces (profiles/r1_trace_*.txt):
+            //   staging ~ tasks per producer warp x (rows per segment + 13 warm-up rows) x 310 cycles
+            //   MMA     ~ S x taps x K-steps x max(120, N) cycles (one issuing thread)
+            // Measured on the k = 11, C = 64 layers: 29 K + 20 K cycles in series -> 2.20 ms; overlapped -> 1.95 ms.
+            // (A full cost model over every (S, buffers, panels) was tried and lost on the C >= 128 layers, whose
+            // weight re-streaming per tile it underestimates.)
+            if (tall_first && a_bufs == 1 && S > 1 && getenv("TB200_SNAKE_PLAN_OLD") == nullptr) {
+              const int n_prod = Roles<true>::kWorkers - 8;
+              const int ncb = a.Cin_pad / 32;
+              int g = ncb > 0 ? ncb : 1, r2 = n_prod;
+              while (r2) { const int t = g % r2; g = r2; r2 = t; }
+              const int nseg = n_prod / g;
+              const double stage = (double)((ncb * nseg + n_prod - 1) / n_prod) * ((double)R / nseg + 13.0) * 310.0;
+              const double mma = (double)S * a.ntaps * (a.Cin_pad / 16) * (a.NT > 120 ? a.NT : 120);
+              const long long budget2 = (long long)smem_cap - fixed - 2LL * a_bytes;
+              const long long slots = budget2 > 0 ? budget2 / c.chunk_bytes : 0;
+              if (mma >= 0.5 * stage && slots >= 4) {
+                c.a_bufs = 2;
+                c.resident = 0;
+                c.ring_slots = (int)(slots > 8 ? 8 : slots);
+              }
+            }
             a = c;
             return 0;
           }
@@ -1463,6 +1487,10 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
     if (v >= 2 && v <= kMaxProdWarps && (w - v == 4 || w - v == 8)) a.n_prod = v;
   }
   const int smem_bytes = ws_layout(a).total;
+  if (getenv("TB200_PLAN_DEBUG"))
+    fprintf(stderr, "tb200 plan: Cin=%d Cout=%d taps=%d up=%d act=%d L=%d -> S=%d a_bufs=%d acc_bufs=%d panels=%d ntiles=%d %s ring=%d n_prod=%d smem=%d\n",
+            a.Cin, a.Cout, a.ntaps, a.up, a.act, p->L_in_max, a.S, a.a_bufs, a.acc_bufs, a.n_panels, a.n_ntiles,
+            a.resident ? "resident" : "streamed", a.ring_slots, a.n_prod, smem_bytes);
   if (smem_bytes > g_max_smem / ctas) return fail(TB200_E_NOSMEM, "conv1d: %d bytes of shared memory", smem_bytes);
   if (p->precision == TB200_PREC_F16)
     return snake ? launch_t<__half, true, ctas>(a, smem_bytes, stream) : launch_t<__half, false, ctas>(a, smem_bytes, stream);

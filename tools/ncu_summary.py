@@ -67,5 +67,29 @@ def launch_list(path, out):
     open(out, "w").write("\n".join(lines) + "\n")
 
 
+def step_list(path, out):
+    """Launch list with time + DRAM bytes per launch (three metrics per kernel id); also prints the mean traffic."""
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ii, ki, bi, mi, vi = (hdr.index(k) for k in ("ID", "Kernel Name", "Block Size", "Metric Name", "Metric Value"))
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        d = per.setdefault(r[ii], {"name": r[ki].split("(")[0].replace("void ", "").replace("tb200::", ""), "block": r[bi]})
+        d[r[mi]] = float(r[vi].replace(",", ""))
+    tot_ns = sum(d["gpu__time_duration.sum"] for d in per.values())
+    rd = sum(d["dram__bytes_read.sum"] for d in per.values())
+    wr = sum(d["dram__bytes_write.sum"] for d in per.values())
+    lines = [f"# ncu launch list of ONE timed BigVGAN step (bench.py --steps 1 --no-cpu-baseline; ncu -k regex:conv1d_umma -s 234 -c 78): {len(per)} launches",
+             "# metrics: gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum (cold-cache, serialised: compare shares)",
+             f"# total {tot_ns / 1e6:.3f} ms, DRAM read {rd / 1e9:.2f} GB, write {wr / 1e9:.2f} GB -> {(rd + wr) / len(per) / 1e6:.1f} MB per launch",
+             f"{'#':>3s} {'kernel':44s} {'block':>13s} {'us':>10s} {'share':>6s} {'rd MB':>9s} {'wr MB':>9s}"]
+    for i, d in enumerate(per.values()):
+        ns = d["gpu__time_duration.sum"]
+        lines.append(f"{i:3d} {d['name'][:44]:44s} {d['block']:>13s} {ns / 1e3:10.1f} {100 * ns / tot_ns:5.1f}% "
+                     f"{d['dram__bytes_read.sum'] / 1e6:9.1f} {d['dram__bytes_write.sum'] / 1e6:9.1f}")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print(f"mean DRAM traffic per launch: {int((rd + wr) / len(per))} bytes")
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "list": launch_list, "steplist": step_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
