@@ -12,7 +12,8 @@ TOL = {"fp32": 2e-5, "tf32": 2e-3, "f16": 2e-3}
 
 
 def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0, snake=False, residual=False,
-         out_act=0, out_alpha=1.0, res_beta=1.0, accumulate=False, x_half=False, y_half=False, seed=0):
+         out_act=0, out_alpha=1.0, res_beta=1.0, accumulate=False, x_half=False, y_half=False, seed=0,
+         y_misalign=False):
     from ims_toucan_prosody_variance_b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, Cin, L, generator=g)
@@ -60,6 +61,10 @@ def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0,
     yd = y0.to(cuda)
     if y_half:
         yd = yd.half()
+    if y_misalign:   # a view whose rows start one element off: no 8-byte (fp32) / 4-byte (fp16) alignment for paired stores
+        full = torch.zeros(B, Cout, Lout + 2 + (Lout & 1), dtype=yd.dtype, device=cuda)
+        full[:, :, 1:1 + Lout] = yd
+        yd = full[:, :, 1:1 + Lout]
     lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
     layer(xd, lt, yd, act=2 if snake else act, slope=slope, alpha=alpha.to(cuda) if snake else None,
           beta=beta.to(cuda) if snake else None, out_act=out_act, out_alpha=out_alpha,
@@ -171,3 +176,22 @@ def test_wide_linear_relu_and_scaled_residual(cuda, prec):
         rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
         assert rel < 2e-3, f"{prec} b={b} rel rms err {rel:.3e}"
         assert torch.equal(y[b, :, n:].cpu(), x[b, :, n:])
+
+
+@pytest.mark.parametrize("u,cin,cout", [(4, 64, 32), (8, 32, 16), (2, 32, 16), (6, 64, 64)])
+@pytest.mark.parametrize("y_half", [False, True])
+def test_transposed_store_only_epilogue(cuda, u, cin, cout, y_half):
+    """Every up-sampling stride of the vocoders through the stride-templated epilogue: fp32 / fp16 outputs, ragged batch
+    with a 1-frame utterance, odd lengths."""
+    _run(cuda, "f16", B=3, Cin=cin, Cout=cout, K=2 * u, dil=1, L=333, lens=[333, 1, 150], up=u, y_half=y_half)
+
+
+@pytest.mark.parametrize("u", [4, 8])
+@pytest.mark.parametrize("y_half", [False, True])
+def test_transposed_unaligned_output_rows(cuda, u, y_half):
+    """Output rows that are not 8-byte aligned take the scalar-store variant of the same epilogue."""
+    _run(cuda, "f16", B=2, Cin=32, Cout=16, K=2 * u, dil=1, L=130, lens=[130, 61], up=u, y_half=y_half, y_misalign=True)
+
+
+def test_transposed_with_residual_keeps_generic_epilogue(cuda):
+    _run(cuda, "f16", B=2, Cin=64, Cout=32, K=8, dil=1, L=150, lens=[150, 40], up=4, residual=True, res_beta=0.5)
