@@ -1475,6 +1475,7 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
       t.a_bytes = a.a_bytes / a.R * t.R;
       t.tiles_per_utt = (rows_max + cap * kTileM - 1) / (cap * kTileM);
       t.total_tiles = t.tiles_per_utt * a.B;
+      t.acc_bufs = 2 * cap * a.NT <= 512 ? 2 : 1;
       int cols = 32;
       while (cols < t.acc_bufs * cap * a.NT) cols <<= 1;
       t.tmem_cols = cols;
