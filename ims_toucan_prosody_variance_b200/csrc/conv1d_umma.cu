@@ -1114,33 +1114,38 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     }
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The whole warp runs this loop convergently and lane 0 alone issues tcgen05.mma / commit: every operand is then
+    // warp-uniform (uniform registers), where a lane-0-only region made the compiler wrap each MMA in an
+    // ELECT / R2UR.BROADCAST waterfall (~18 instructions, ~115 cycles per MMA against 48-64 of the tensor pipe).
+    {
       const uint32_t idesc = make_instr_desc(a.NT, kTf32);
       const uint32_t lbo_a = a.R * 16, lbo_b = a.NT * 16;
       const uint32_t desc_hi = smem_desc_hi(128);
       const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;   // descriptor units (16 bytes) per K step
       const uint32_t smW_u = smem_u32(smW);
       uint32_t ai = 0, ac = 0, cc = 0;
-      long long w_wait = 0;   // cycles the issuer spent waiting for streamed weight chunks (trace only)
+      long long w_wait = 0;   // cycles the MMA warp spent waiting for streamed weight chunks (trace only)
       bool first_tile = true;
       uint32_t a_buf_cur = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_utt;
         const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-        const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+        const int len = __shfl_sync(0xffffffffu, a.len_in ? __ldg(a.len_in + b) : a.L_in_max, 0);
         const int rows = len + extra_row;
         if (t0 >= rows || len <= 0) continue;
         const int nsub = min(a.S, (rows - t0 + kTileM - 1) / kTileM);
         for (int nt = 0; nt < a.n_ntiles; ++nt, ++ac) {
           const int abuf = ac % a.acc_bufs;
           mbar_wait(acc_empty + abuf, ((ac / a.acc_bufs) & 1) ^ 1);
-          trace(a, 6, ac);
+          __syncwarp();
+          if (lane == 0) trace(a, 6, ac);
           const uint32_t acc_col = tmem_base + (uint32_t)(abuf * a.S * a.NT);
           for (int pn = 0; pn < a.n_panels; ++pn) {
             if (restage_per_nt || nt == 0) {
               a_buf_cur = ai % a.a_bufs;
               mbar_wait(a_full + a_buf_cur, (ai / a.a_bufs) & 1);
-              trace(a, 2, ai);
+              __syncwarp();
+              if (lane == 0) trace(a, 2, ai);
               ++ai;
             }
             tc_fence_after();
@@ -1152,11 +1157,13 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                 if (a.resident) {
                   slot = (nt * a.ntaps + j) * a.n_kchunks + pn * kc_per_panel + kcl;
                   if (first_tile) mbar_wait(w_full + slot, 0);
+                  __syncwarp();
                 } else {
                   slot = cc % a.ring_slots;
                   const long long tw = a.trace ? clock64() : 0;
                   mbar_wait(w_full + slot, (cc / a.ring_slots) & 1);
                   if (a.trace) w_wait += clock64() - tw;
+                  __syncwarp();
                 }
                 tc_fence_after();
                 const uint32_t b_base = smW_u + (uint32_t)slot * (uint32_t)a.chunk_bytes;
@@ -1169,21 +1176,21 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                 for (int sub = 0; sub < nsub; ++sub) {
                   uint32_t a_lo = a_lo0 + (uint32_t)(sub * kTileM), b_lo = b_lo0;   // 16 bytes per row -> +1 per row
                   const uint32_t d_col = acc_col + (uint32_t)(sub * a.NT);
-                  umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
+                  if (elect_one()) umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
                   for (int ks = 1; ks < nks; ++ks) {
                     a_lo += a_kstep;
                     b_lo += b_kstep;
-                    umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
+                    if (elect_one()) umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
                   }
                 }
-                if (!a.resident) umma_commit(w_empty + slot);
+                if (!a.resident && elect_one()) umma_commit(w_empty + slot);
               }
             }
-            if (restage_per_nt || nt == a.n_ntiles - 1) umma_commit(a_empty + a_buf_cur);
+            if ((restage_per_nt || nt == a.n_ntiles - 1) && elect_one()) umma_commit(a_empty + a_buf_cur);
           }
-          umma_commit(acc_full + abuf);
-          trace(a, 3, ac);
-          if (a.trace && blockIdx.x == 0 && ac < (uint32_t)kTraceTiles) a.trace[ac * 8 + 7] = w_wait;   // cumulative
+          if (elect_one()) umma_commit(acc_full + abuf);
+          if (lane == 0) trace(a, 3, ac);
+          if (lane == 0 && a.trace && blockIdx.x == 0 && ac < (uint32_t)kTraceTiles) a.trace[ac * 8 + 7] = w_wait;   // cumulative
         }
         first_tile = false;
       }
