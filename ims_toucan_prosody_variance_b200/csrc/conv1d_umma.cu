@@ -1375,8 +1375,9 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
             // When the MMAs are a large part of a tile (many taps), stream the weights through a small ring instead
             // and double-buffer the staging -- estimated from the in-kernel traces (profiles/r1_trace_*.txt):
             //   staging ~ tasks per producer warp x (rows per segment + 13 warm-up rows) x 310 cycles
-            //   MMA     ~ S x taps x K-steps x max(120, N) cycles (one issuing thread)
-            // Measured on the k = 11, C = 64 layers: 29 K + 20 K cycles in series -> 2.20 ms; overlapped -> 1.95 ms.
+            //   MMA     ~ S x taps x K-steps x max(70, N) cycles (one issuing thread)
+            // Measured on the k = 11, C = 64 layers: 29 K + 20 K cycles in series -> 2.20 ms; overlapped -> 1.95 ms
+            // (MMA issue has since dropped to 12 K cycles; the rule fires from 30 % of the staging time).
             // (A full cost model over every (S, buffers, panels) was tried and lost on the C >= 128 layers, whose
             // weight re-streaming per tile it underestimates.)
             if (tall_first && a_bufs == 1 && S > 1 && getenv("TB200_SNAKE_PLAN_OLD") == nullptr) {
@@ -1386,10 +1387,10 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
               while (r2) { const int t = g % r2; g = r2; r2 = t; }
               const int nseg = n_prod / g;
               const double stage = (double)((ncb * nseg + n_prod - 1) / n_prod) * ((double)R / nseg + 13.0) * 310.0;
-              const double mma = (double)S * a.ntaps * (a.Cin_pad / 16) * (a.NT > 120 ? a.NT : 120);
+              const double mma = (double)S * a.ntaps * (a.Cin_pad / 16) * (a.NT > 70 ? a.NT : 70);
               const long long budget2 = (long long)smem_cap - fixed - 2LL * a_bytes;
               const long long slots = budget2 > 0 ? budget2 / c.chunk_bytes : 0;
-              if (mma >= 0.5 * stage && slots >= 4) {
+              if (mma >= 0.3 * stage && slots >= 4) {
                 c.a_bufs = 2;
                 c.resident = 0;
                 c.ring_slots = (int)(slots > 8 ? 8 : slots);
