@@ -1084,19 +1084,22 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     }
   } else if (warp == kLoadWarp) {
     // ================================ weight loader ================================
-    if (lane == 0) {
+    // (whole warp convergent, one elected lane issues: see the MMA issuer)
+    {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w);
       if (a.resident) {
         for (int c = 0; c < a.n_chunks; ++c) {
-          mbar_arrive_expect_tx(w_full + c, a.chunk_bytes);
-          bulk_copy_g2s(smW + (long long)c * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes, w_full + c);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(w_full + c, a.chunk_bytes);
+            bulk_copy_g2s(smW + (long long)c * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes, w_full + c);
+          }
         }
       } else {
         uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
           const int b = tile / a.tiles_per_utt;
           const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-          const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+          const int len = __shfl_sync(0xffffffffu, a.len_in ? __ldg(a.len_in + b) : a.L_in_max, 0);
           if (t0 >= len + extra_row || len <= 0) continue;
           for (int nt = 0; nt < a.n_ntiles; ++nt)
             for (int pn = 0; pn < a.n_panels; ++pn)
@@ -1105,9 +1108,12 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                   const int c = (nt * a.ntaps + j) * a.n_kchunks + pn * kc_per_panel + kcl;
                   const int slot = cc % a.ring_slots;
                   mbar_wait(w_empty + slot, ((cc / a.ring_slots) & 1) ^ 1);
-                  mbar_arrive_expect_tx(w_full + slot, a.chunk_bytes);
-                  bulk_copy_g2s(smW + (long long)slot * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes,
-                                w_full + slot);
+                  __syncwarp();
+                  if (elect_one()) {
+                    mbar_arrive_expect_tx(w_full + slot, a.chunk_bytes);
+                    bulk_copy_g2s(smW + (long long)slot * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes,
+                                  w_full + slot);
+                  }
                 }
         }
       }
