@@ -1179,17 +1179,20 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
                 // instruction bound: ~30 dependent integer ops per MMA measured 160-290 cycles per MMA)
                 const uint32_t a_lo0 = smem_desc_lo(a_base, lbo_a), b_lo0 = smem_desc_lo(b_base, lbo_b);
                 const int nks = a.KC / kStepK;
-                for (int sub = 0; sub < nsub; ++sub) {
-                  uint32_t a_lo = a_lo0 + (uint32_t)(sub * kTileM), b_lo = b_lo0;   // 16 bytes per row -> +1 per row
-                  const uint32_t d_col = acc_col + (uint32_t)(sub * a.NT);
-                  if (elect_one()) umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
-                  for (int ks = 1; ks < nks; ++ks) {
-                    a_lo += a_kstep;
-                    b_lo += b_kstep;
-                    if (elect_one()) umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
+                if (elect_one()) {   // one leader issues every MMA of this weight chunk
+                  for (int sub = 0; sub < nsub; ++sub) {
+                    uint32_t a_lo = a_lo0 + (uint32_t)(sub * kTileM), b_lo = b_lo0;   // 16 bytes per row -> +1 per row
+                    const uint32_t d_col = acc_col + (uint32_t)(sub * a.NT);
+                    umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
+                    for (int ks = 1; ks < nks; ++ks) {
+                      a_lo += a_kstep;
+                      b_lo += b_kstep;
+                      umma_ss_lohi<kTf32>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, 1u);
+                    }
                   }
+                  if (!a.resident) umma_commit(w_empty + slot);
                 }
-                if (!a.resident && elect_one()) umma_commit(w_empty + slot);
+                __syncwarp();
               }
             }
             if ((restage_per_nt || nt == a.n_ntiles - 1) && elect_one()) umma_commit(a_empty + a_buf_cur);
