@@ -65,6 +65,16 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+            return
+        # wait (bounded) for the first sample: nvidia-smi has then finished its start-up
+        t_end = time.time() + 5.0
+        while time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -224,15 +234,17 @@ def run_tts_workload(args, rank, local_rank, world, dev, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the clock sampler (an nvidia-smi process) starts BEFORE the warm-up: its start-up takes driver locks for tens of
+    # milliseconds, which must not land inside the timed region; samples are taken through warm-up and timed steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         out, out_len, r = step(text_dev)
     barrier()
     frames = [int(v) for v in r["frames_host"]]
     audio_s = sum(2 * (f // 2) for f in frames) * SAMPLES_PER_FRAME / SAMPLE_RATE
     launches0 = ops.LAUNCHES
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -373,13 +385,15 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ----
+    # the clock sampler (an nvidia-smi process) starts BEFORE the warm-up: its start-up takes driver locks for tens of
+    # milliseconds, which must not land inside the timed region; samples are taken through warm-up and timed steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         model.forward_batch(mel_dev, lengths)
     barrier()
     launches0 = ops.LAUNCHES
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
