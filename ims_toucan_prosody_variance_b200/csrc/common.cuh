@@ -119,7 +119,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One leader lane of a converged warp (elect.sync picks the same lane for the same mask): the compiler then knows a single
+// One leader lane of a converged warp.  elect.sync is deterministic: the same leader for the same member mask every
+// time, so the thread that issues the MMAs is also the one whose tcgen05.commit tracks them.  The compiler knows a single
 // thread executes the guarded code and feeds tcgen05 instructions from uniform registers without a broadcast loop.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
