@@ -1399,7 +1399,9 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
               const double mma = (double)S * a.ntaps * (a.Cin_pad / 16) * (a.NT > 70 ? a.NT : 70);
               const long long budget2 = (long long)smem_cap - fixed - 2LL * a_bytes;
               const long long slots = budget2 > 0 ? budget2 / c.chunk_bytes : 0;
-              if (mma >= 0.3 * stage && slots >= 4) {
+              double ratio = 0.3;
+              if (const char* e = getenv("TB200_SNAKE_A2_RATIO")) ratio = atof(e);   // tuning knob
+              if (mma >= ratio * stage && slots >= 4) {
                 c.a_bufs = 2;
                 c.resident = 0;
                 c.ring_slots = (int)(slots > 8 ? 8 : slots);
