@@ -30,12 +30,27 @@ class Conv1dParams(ctypes.Structure):
     ]
 
 
+class RespairParams(ctypes.Structure):
+    """struct tb200_respair_params (include/toucan_b200.h)."""
+    _fields_ = [
+        ("x", c_void_p), ("x_dtype", c_int), ("x_bs", c_int64), ("x_ld", c_int), ("len", c_void_p),
+        ("B", c_int), ("C", c_int), ("L_max", c_int), ("K", c_int), ("dilation", c_int),
+        ("w1_packed", c_void_p), ("bias1", c_void_p), ("w2_packed", c_void_p), ("bias2", c_void_p),
+        ("act", c_int), ("act_slope", c_float),
+        ("act1_alpha", c_void_p), ("act1_beta", c_void_p), ("act2_alpha", c_void_p), ("act2_beta", c_void_p),
+        ("out_alpha", c_float), ("res_beta", c_float), ("accumulate", c_int),
+        ("y", c_void_p), ("y_dtype", c_int), ("y_bs", c_int64), ("y_ld", c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/toucan_b200.h declares
 SIGNATURES = {
     "tb200_version": (c_int, []),
     "tb200_last_error": (ctypes.c_char_p, []),
     "tb200_sm_count": (c_int, []),
     "tb200_conv1d": (c_int, [ctypes.POINTER(Conv1dParams), c_void_p]),
+    "tb200_respair": (c_int, [ctypes.POINTER(RespairParams), c_void_p]),
+    "tb200_respair_trace_read": (c_int, [c_void_p, c_int]),
     "tb200_packed_weight_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "tb200_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tb200_duration_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,

@@ -27,7 +27,9 @@ int fail(int code, const char* fmt, ...);
 // anti-aliasing filter of alias_free_torch.Activation1d: kaiser_sinc_filter1d(0.25, 0.3, 12)
 // (symmetric, sums to 1).  Filled at library load (api.cu) from the closed form, in double.
 // ---------------------------------------------------------------------------------------------
-__constant__ float c_aa_filter[12];  // single translation unit (toucan_b200.cu)
+#ifndef TB200_NO_AA_CONSTANT   // defined once, in the translation unit that also uploads it (toucan_b200.cu)
+__constant__ float c_aa_filter[12];
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -58,7 +60,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 // Bounded wait: a desynchronised pipeline traps (launch failure) instead of hanging the GPU.
-__device__ __noinline__ void mbar_timeout() {
+static __device__ __noinline__ void mbar_timeout() {
   printf("tb200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
 }

@@ -160,6 +160,7 @@ __device__ __forceinline__ void stage_pointwise(const ConvArgs& a, int b, int t_
 // A warp handles one channel group for 26 consecutive rows per pass: all 32 lanes produce the 64
 // s values those 26 outputs need into a per-warp scratch line, then lanes 0..25 run the 12-tap
 // down filter.  scratch: nwarps * 2 * kAaScratch floats.
+#ifndef TB200_NO_AA_CONSTANT
 template <int E, bool kFast, typename Store>
 __device__ __forceinline__ void stage_aa_snake(const ConvArgs& a, int b, int t_lo, int R, int g0, int ng, int len,
                                                const Store& st, float* scratch, int warp, int nwarps, int lane) {
@@ -242,6 +243,7 @@ __device__ __forceinline__ void stage_aa_snake(const ConvArgs& a, int b, int t_l
   }
   __syncwarp();
 }
+#endif  // TB200_NO_AA_CONSTANT
 
 // ---------------------------------------------------------------------------------------------
 // epilogue arithmetic shared by both implementations

@@ -96,6 +96,56 @@ class ConvLayer:
         return out
 
 
+class ResPair:
+    """One residual pair  x + conv2(ACT2(conv1(ACT1(x))))  as a single tb200_respair launch
+    (AMP.py:51-60, ResidualBlock.py:93-97).  conv1 / conv2: ConvLayer objects packed with precision 'f16'
+    (same channel count and kernel size; conv2 has dilation 1).  act1 / act2: (alpha, beta) tensors for the
+    anti-aliased SnakeBeta, or None for LeakyReLU."""
+
+    def __init__(self, conv1, conv2, act1=None, act2=None):
+        if conv1.precision != PREC_F16 or conv2.precision != PREC_F16:
+            raise _lib.EngineError("ResPair needs fp16-operand ConvLayers")
+        if not (conv1.c_in == conv1.c_out == conv2.c_in == conv2.c_out and conv1.k == conv2.k and conv2.dilation == 1
+                and conv1.up == 0 and conv2.up == 0 and conv1.pad == (conv1.k - 1) // 2 * conv1.dilation
+                and conv2.pad == (conv2.k - 1) // 2):
+            raise _lib.EngineError("ResPair: the two convolutions must be 'same'-padded C->C with one kernel size")
+        self.c1, self.c2, self.act1, self.act2 = conv1, conv2, act1, act2
+        self._p = _lib.RespairParams()
+
+    @staticmethod
+    def supported(channels, precision):
+        return precision in ("f16", PREC_F16) and channels in (32, 64, 128)
+
+    def __call__(self, x, lengths, out, l_max=None, slope=0.1, out_alpha=1.0, res_beta=1.0, accumulate=False):
+        """x (B,C,L) -> out (B,C,L), NCL with contiguous rows, fp32 or fp16; out must not alias x."""
+        global LAUNCHES
+        _require_cuda(x, out, lengths)
+        c = self.c1.c_in
+        if x.stride(2) != 1 or out.stride(2) != 1 or x.shape[1] != c or out.shape[1] != c:
+            raise _lib.EngineError(f"respair: bad tensor layout x={tuple(x.shape)} out={tuple(out.shape)} C={c}")
+        p = self._p
+        p.x, p.x_dtype, p.x_bs, p.x_ld = x.data_ptr(), _dtype_code(x), x.stride(0), x.stride(1)
+        p.len = lengths.data_ptr() if lengths is not None else None
+        p.B, p.C, p.L_max = x.shape[0], c, int(l_max if l_max is not None else x.shape[2])
+        p.K, p.dilation = self.c1.k, self.c1.dilation
+        p.w1_packed, p.bias1 = self.c1.packed.data_ptr(), (self.c1.bias.data_ptr() if self.c1.bias is not None else None)
+        p.w2_packed, p.bias2 = self.c2.packed.data_ptr(), (self.c2.bias.data_ptr() if self.c2.bias is not None else None)
+        if self.act1 is not None:
+            p.act, p.act_slope = ACT_AA_SNAKEBETA, 0.0
+            p.act1_alpha, p.act1_beta = self.act1[0].data_ptr(), self.act1[1].data_ptr()
+            p.act2_alpha, p.act2_beta = self.act2[0].data_ptr(), self.act2[1].data_ptr()
+        else:
+            p.act, p.act_slope = ACT_LEAKY_RELU, slope
+            p.act1_alpha = p.act1_beta = p.act2_alpha = p.act2_beta = None
+        p.out_alpha, p.res_beta, p.accumulate = out_alpha, res_beta, int(accumulate)
+        p.y, p.y_dtype, p.y_bs, p.y_ld = out.data_ptr(), _dtype_code(out), out.stride(0), out.stride(1)
+        if p.L_max > out.shape[2] or p.L_max > x.shape[2]:
+            raise _lib.EngineError("respair: buffers shorter than L_max")
+        _lib.check(_lib.load().tb200_respair(ctypes.byref(p), _lib.stream_ptr()), "tb200_respair")
+        LAUNCHES += 1
+        return out
+
+
 def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1.0, duration_scale=1.0, t_ld=None):
     """text (B,T,62) fp32, text_len (B) int32, log_dur (B,T_ld) fp32 or gold_dur (B,T_ld) int64 (T_ld >= T, row pitch).
     Returns durations (B,T_ld) int64, inclusive prefix sums (B,T_ld) int32, frames (B) int32."""

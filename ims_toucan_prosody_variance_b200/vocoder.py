@@ -6,10 +6,12 @@ the reference; `forward(c)` keeps the reference's batch-1 contract ((80,T) -> (T
 `forward_batch` is the additive batched entry ((B,80,T) + per-utterance lengths), whose result for
 each utterance equals a batch-1 call (zero / replicate padding at the utterance's own ends).
 
-Every convolution of the generator is one tb200_conv1d launch with its activation fused in the
-prologue (LeakyReLU, or BigVGAN's anti-aliased SnakeBeta) and bias / residual / the 1/3 multi-
-receptive-field mean fused in the epilogue.  The residual stream stays fp32 in HBM; the value between
-the two convs of a residual pair is stored as fp16 (it is only ever consumed as a tensor-core operand).
+Residual pairs (act -> conv_d -> act -> conv_1 -> +x: AMP.py:51-60, ResidualBlock.py:93-97) of the stages
+with <= 128 channels are ONE tb200_respair launch each: the tensor between the two convolutions never
+leaves the SM, and the 1/3 multi-receptive-field mean is folded into the last pair of a block.  Every
+other convolution (input / output convs, up-samplers, the 256-channel stage) is one tb200_conv1d launch
+with its activation fused in the prologue and bias / residual / mean in the epilogue.
+fuse_pairs=False keeps the two-launch form of every pair (fp16 tensor between the convs through HBM).
 """
 import torch
 
@@ -30,11 +32,12 @@ class _GeneratorBase(torch.nn.Module):
 
     upsample_scales = (8, 6, 4, 2)
 
-    def _init_engine(self, precision, activation_dtype="f32"):
+    def _init_engine(self, precision, activation_dtype="f32", fuse_pairs=True):
         if activation_dtype not in ("f32", "f16") or (activation_dtype == "f16" and precision != "f16"):
             raise ops._lib.EngineError("activation_dtype must be 'f32', or 'f16' together with precision='f16'")
         self.precision = precision
         self.activation_dtype = activation_dtype   # storage type of the residual stream in HBM
+        self.fuse_pairs = bool(fuse_pairs)
         self._packed = None
         self._buffers_cache = {}
 
@@ -78,12 +81,22 @@ class _GeneratorBase(torch.nn.Module):
                         for which, idx in (("a1", 2 * m), ("a2", 2 * m + 1)):
                             a = n["act"].format(blk, idx)
                             pk[f"b{blk}.{which}.{m}"] = (sd[a + ".alpha"].float().contiguous(), sd[a + ".beta"].float().contiguous())
+                    if self._pair_fused(self._stage_channels(i), kr):
+                        pk[f"b{blk}.pair.{m}"] = ops.ResPair(pk[f"b{blk}.c1.{m}"], pk[f"b{blk}.c2.{m}"],
+                                                             pk.get(f"b{blk}.a1.{m}"), pk.get(f"b{blk}.a2.{m}"))
         pk["post"] = ops.ConvLayer(sd[n["post"] + ".weight"], sd[n["post"] + ".bias"], padding=(self.kernel_size - 1) // 2,
                                    precision=prec)
         if n["act_post"] is not None:
             pk["post_act"] = (sd[n["act_post"] + ".alpha"].float().contiguous(), sd[n["act_post"] + ".beta"].float().contiguous())
         self._packed = pk
         self._buffers_cache = {}
+
+    def _pair_fused(self, channels, kernel):
+        """Which residual pairs run as one tb200_respair launch.  The 128-channel pairs keep their X tile in shared
+        memory next to two operand tiles: that fits with fp16 streams only."""
+        if not (self.fuse_pairs and ops.ResPair.supported(channels, self.precision)):
+            return False
+        return channels <= 64 or self.activation_dtype == "f16"
 
     # -- workspace ---------------------------------------------------------------------------
     def _workspace(self, b, frames, dev):
@@ -94,7 +107,7 @@ class _GeneratorBase(torch.nn.Module):
             # residual stream: fp32 (default) or fp16 (activation_dtype="f16": halves the HBM bytes per element; every
             # value is rounded to 11 bits once more per layer -- measured SNR in tests/test_vocoder_gpu.py)
             sdt = torch.float16 if self.activation_dtype == "f16" else torch.float32
-            pad = _pad8 if sdt == torch.float16 else _pad4
+            pad = _pad8   # 16-byte aligned rows for either type (vector loads, bulk copies of tb200_respair)
             ws = {"h": torch.zeros((b, self.channels, pad(frames)), dtype=sdt, device=dev)}
             length = frames
             for i, u in enumerate(self.upsample_scales):
@@ -140,11 +153,19 @@ class _GeneratorBase(torch.nn.Module):
                 cur = up
                 ndil = len(self.resblock_dilations[j])
                 for m in range(ndil):
+                    last = m == ndil - 1
+                    pair = pk.get(f"b{blk}.pair.{m}")
+                    if pair is not None:
+                        if last:  # fold the branch into the multi-receptive-field mean
+                            pair(cur, len_t, total, l_max=length, slope=0.1, out_alpha=1.0 / nblk, res_beta=1.0 / nblk,
+                                 accumulate=j > 0)
+                        else:
+                            cur = pair(cur, len_t, ws[f"r{m % 2}{i}"], l_max=length, slope=0.1)
+                        continue
                     a1 = pk.get(f"b{blk}.a1.{m}", (None, None))
                     a2 = pk.get(f"b{blk}.a2.{m}", (None, None))
                     xt = pk[f"b{blk}.c1.{m}"](cur, len_t, ws[f"t{i}"], l_in_max=length, act=res_act, slope=0.1,
                                               alpha=a1[0], beta=a1[1])
-                    last = m == ndil - 1
                     if last:  # fold the branch into the multi-receptive-field mean
                         pk[f"b{blk}.c2.{m}"](xt, len_t, total, l_in_max=length, act=res_act, slope=0.1, alpha=a2[0],
                                              beta=a2[1], out_alpha=1.0 / nblk, residual=cur, res_beta=1.0 / nblk,
@@ -174,7 +195,7 @@ class HiFiGANGenerator(_GeneratorBase):
                  upsample_scales=(8, 6, 4, 2), upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
                  resblock_dilations=((1, 3, 5), (1, 3, 5), (1, 3, 5)), use_additional_convs=True, bias=True,
                  nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
-                 use_weight_norm=True, precision="f16", activation_dtype="f32"):
+                 use_weight_norm=True, precision="f16", activation_dtype="f32", fuse_pairs=True):
         super().__init__()
         if not (use_additional_convs and bias and use_weight_norm and nonlinear_activation == "LeakyReLU"
                 and nonlinear_activation_params.get("negative_slope", 0.1) == 0.1 and out_channels == 1):
@@ -185,7 +206,7 @@ class HiFiGANGenerator(_GeneratorBase):
         lay, alias = layouts.hifigan_layout(in_channels, out_channels, channels, kernel_size, upsample_scales,
                                             upsample_kernel_sizes, resblock_kernel_sizes, resblock_dilations)
         layouts.attach(self, lay, alias)
-        self._init_engine(precision, activation_dtype)
+        self._init_engine(precision, activation_dtype, fuse_pairs)
         if path_to_weights is not None:
             self.load_state_dict(torch.load(path_to_weights, map_location="cpu")["generator"])
 
@@ -208,7 +229,8 @@ class BigVGAN(_GeneratorBase):
 
     def __init__(self, path_to_weights, num_mels=80, upsample_initial_channel=512, upsample_rates=(8, 6, 4, 2),
                  upsample_kernel_sizes=(16, 12, 8, 4), resblock_kernel_sizes=(3, 7, 11),
-                 resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), precision="f16", activation_dtype="f32"):
+                 resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), precision="f16", activation_dtype="f32",
+                 fuse_pairs=True):
         super().__init__()
         self.in_channels, self.channels, self.kernel_size = num_mels, upsample_initial_channel, 7
         self.upsample_scales, self.upsample_kernel_sizes = tuple(upsample_rates), tuple(upsample_kernel_sizes)
@@ -220,7 +242,7 @@ class BigVGAN(_GeneratorBase):
         lay, alias = layouts.bigvgan_layout(num_mels, upsample_initial_channel, upsample_rates, upsample_kernel_sizes,
                                             resblock_kernel_sizes, resblock_dilation_sizes, filter_buffers=has_filters)
         layouts.attach(self, lay, alias)
-        self._init_engine(precision, activation_dtype)
+        self._init_engine(precision, activation_dtype, fuse_pairs)
         if sd is not None:
             self.load_state_dict(sd)
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TB200_VERSION 101
+#define TB200_VERSION 102
 
 enum {
   TB200_OK = 0,
@@ -117,6 +117,48 @@ typedef struct tb200_conv1d_params {
 } tb200_conv1d_params;
 
 int tb200_conv1d(const tb200_conv1d_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tb200_respair -- one residual pair of the vocoder generators in ONE launch; the tensor between the
+ * two convolutions never leaves the SM.  Replaces the loop body
+ *     xt = a1(x); xt = c1(xt); xt = a2(xt); xt = c2(xt); x = xt + x
+ *   BigVGAN AMPBlock1.forward   TrainingInterfaces/Spectrogram_to_Wave/BigVGAN/AMP.py:51-60
+ *   HiFiGAN HiFiGANResidualBlock.forward   Layers/ResidualBlock.py:93-97
+ * and, through out_alpha / res_beta / accumulate, the multi-receptive-field mean of
+ * InferenceAvocodo.py:75-78 / InferenceBigVGAN.py:82-89:
+ *   y[b][c][t] = out_alpha * (b2[c] + conv2(ACT2(b1 + conv1(ACT1(x))))[b][c][t]) + res_beta * x[b][c][t]
+ *              (+ y_old[b][c][t] if accumulate)                        for 0 <= t < len[b]
+ *   conv1: Conv1d(C, C, K, dilation, padding (K-1)/2*dilation); conv2: Conv1d(C, C, K, padding (K-1)/2).
+ *   ACT: TB200_ACT_LEAKY_RELU (act_slope in [0,1]) or TB200_ACT_AA_SNAKEBETA (per-channel alpha/beta of
+ *   each of the two activations).  ACT(x) and the conv inputs are zero outside [0, len[b]); the
+ *   anti-aliasing filters replicate-pad at the utterance's own ends (batch-1 semantics).
+ * Operands are fp16 (tcgen05 kind::f16, fp32 accumulate): w1/w2 from tb200_pack_conv_weight(C, C, K, 0,
+ * TB200_PREC_F16).  x: 16-byte aligned, row pitch / batch stride multiples of 8 (fp16) or 4 (fp32)
+ * elements, row pitch >= L_max rounded up to that unit.  y must not alias x.  C in {32, 64, 128}.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct tb200_respair_params {
+  const void* x;            /* (B, C, L) NCL residual stream in                         */
+  int32_t x_dtype;          /* TB200_F32 | TB200_F16                                    */
+  int64_t x_bs; int32_t x_ld;
+  const int32_t* len;       /* (B) valid lengths, device; NULL = L_max for all          */
+  int32_t B, C, L_max;
+  int32_t K, dilation;      /* conv1 dilation; conv2 has dilation 1                     */
+  const void* w1_packed; const float* bias1;
+  const void* w2_packed; const float* bias2;
+  int32_t act;              /* TB200_ACT_LEAKY_RELU | TB200_ACT_AA_SNAKEBETA            */
+  float act_slope;
+  const float *act1_alpha, *act1_beta;   /* (C) log-scale snake parameters before conv1 */
+  const float *act2_alpha, *act2_beta;   /* (C) ... before conv2                        */
+  float out_alpha, res_beta;
+  int32_t accumulate;
+  void* y;                  /* (B, C, L) residual stream out                            */
+  int32_t y_dtype; int64_t y_bs; int32_t y_ld;
+} tb200_respair_params;
+
+int tb200_respair(const tb200_respair_params* p, void* stream);
+
+/* Debugging aid: like tb200_debug_trace_read, for tb200_respair (16 stamps per tile).            */
+int tb200_respair_trace_read(int64_t* host_out, int32_t n);
 
 /* Bytes of the packed weight blob for a conv geometry and precision. */
 int64_t tb200_packed_weight_bytes(int32_t C_in, int32_t C_out, int32_t K, int32_t transposed_stride, int32_t precision);
