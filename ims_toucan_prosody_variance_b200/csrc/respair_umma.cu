@@ -58,8 +58,9 @@ struct PairArgs {
   int resident, ring_slots;
   int tiles_per_utt, total_tiles;
   int tmem_cols;
-  int a1_off, a2_off, x_off, scr_off, w_off, bar_off, bias_off, tmem_off, smem_total;
+  int a1_off, a2_off, x_off, scr_off, w_off, bar_off, bias_off, tmem_off, stage_off, smem_total;
   long long* trace;
+  int dbg_skip;           // TB200_PAIR_SKIP (profiling only): 1 no MMAs, 2 no conv2 epilogue body, 4 no conv1 epilogue body
 };
 
 template <bool SNAKE>
@@ -104,43 +105,57 @@ __device__ __forceinline__ bool pair_tile(const PairArgs& a, int tile, PairTile&
 // Every role walks the CTA's tiles in the same order: stage-1 work of tile j, then stage-2 work of tile j-1.
 template <typename F1, typename F2>
 __device__ __forceinline__ void pair_schedule(const PairArgs& a, F1&& stage1, F2&& stage2) {
+  // (one call site per stage: the stage bodies are inlined exactly once)
   PairTile prev{0, 0, 0};
   bool have_prev = false;
   uint32_t j = 0;
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-    PairTile cur;
-    if (!pair_tile(a, tile, cur)) continue;
-    stage1(cur, j);
+  int tile = blockIdx.x;
+#pragma unroll 1
+  for (;;) {
+    PairTile cur{0, 0, 0};
+    bool have_cur = false;
+#pragma unroll 1
+    while (tile < a.total_tiles && !have_cur) {
+      have_cur = pair_tile(a, tile, cur);
+      tile += gridDim.x;
+    }
+    if (have_cur) stage1(cur, j);
     if (have_prev) stage2(prev, j - 1);
+    if (!have_cur) break;
     prev = cur;
     have_prev = true;
     ++j;
   }
-  if (have_prev) stage2(prev, j - 1);
 }
 
 // ---------------------------------------------------------------------------------------------
 // producers
 // ---------------------------------------------------------------------------------------------
+// One copy of the streaming filter per (EDGE, XF16), shared by both activations of the pair: the steady loop alone is
+// ~8 KB of SASS, and with one inlined copy per call site (the first build: 17 K instructions per kernel) the warps
+// running ACT1 and ACT2 side by side thrashed the instruction caches (ncu: `no_instruction` the second largest stall).
+template <bool EDGE, bool XF16>
+__device__ __noinline__ void pair_aa_task(const void* src, long long row, float ea, float ib, int t_lo, int t_beg, int t_end,
+                                          int len, __half* dst) {
+  aa_channel_task<__half, EDGE, XF16, true>(src, row, ea, ib, t_lo, t_beg, t_end, len, dst);
+}
+
 // Anti-aliased SnakeBeta of a [channel][time] shared-memory tile into the K-major operand tile dst ([C/8][Rp][8]):
 // warp pw of np takes one (32-channel block, row segment); src element of channel c at time t = src[c*pitch + t - col0_t].
+// ea_ib: per channel (e^alpha, 1 / (e^beta + 1e-9)), computed once per CTA into shared memory.
 template <bool XF16>
-__device__ __forceinline__ void pair_snake_stage(const void* src, int pitch, int col0_t, const float* __restrict__ alpha,
-                                                 const float* __restrict__ beta, int C, int t_lo, int R, int Rp, int len,
-                                                 __half* dst_tile, int pw, int np, int lane) {
+__device__ __forceinline__ void pair_snake_stage(const void* src, int pitch, int col0_t, const float2* ea_ib, int C, int t_lo,
+                                                 int R, int Rp, int len, __half* dst_tile, int pw, int np, int lane) {
   const int ncb = C >> 5;
   const int nseg = np / ncb;
-  const int seg_rows = (R + nseg - 1) / nseg;
-  // interior boundaries where (t + 6) % 8 == 0: segments then start and end on whole 8-step blocks of the filter
+  // Segments in whole 8-step blocks of the filter, the same number (+-1) for every warp: interior boundaries sit where
+  // (t + 6) % 8 == 0, so only the tile's first and last segment run partial (checked) blocks.
+  const int ph0 = (t_lo + 6) & 7;                  // rows [0, R) span blocks 0 .. nblk-1 of 8 rows starting at row -ph0
+  const int nblk = (R + ph0 + 7) >> 3;
   auto seg_start = [&](int sgm) {
     if (sgm <= 0) return 0;
     if (sgm >= nseg) return R;
-    int r = sgm * seg_rows;
-    if (seg_rows >= 8) {
-      const int ph = (t_lo + r + 6) & 7;
-      r += ph > 4 ? 8 - ph : -ph;
-    }
-    return min(max(r, 0), R);
+    return min(max(((sgm * nblk + nseg / 2) / nseg) * 8 - ph0, 0), R);
   };
   const int cb = pw / nseg, seg = pw - cb * nseg;
   if (cb >= ncb) return;
@@ -155,10 +170,10 @@ __device__ __forceinline__ void pair_snake_stage(const void* src, int pitch, int
   }
   const long long row = (long long)cl * pitch - col0_t;
   const bool edge = (((t_beg - 9) & ~7) < 0) || (t_end + 32 > len);   // warp-uniform
-  const float ea = __expf(__ldg(alpha + cl));
-  const float ib = 1.0f / (__expf(__ldg(beta + cl)) + 1e-9f);
-  if (edge) aa_channel_task<__half, true, XF16, true>(src, row, ea, ib, t_lo, t_beg, t_end, len, dst);
-  else aa_channel_task<__half, false, XF16, true>(src, row, ea, ib, t_lo, t_beg, t_end, len, dst);
+  const float2 pr = ea_ib[cl];
+  const float ea = pr.x, ib = pr.y;
+  if (edge) pair_aa_task<true, XF16>(src, row, ea, ib, t_lo, t_beg, t_end, len, dst);
+  else pair_aa_task<false, XF16>(src, row, ea, ib, t_lo, t_beg, t_end, len, dst);
 }
 
 // LeakyReLU of the X tile into A1: a thread takes 8 channels (one operand group) x 2 consecutive time steps.
@@ -170,6 +185,7 @@ __device__ __forceinline__ void pair_leaky_stage(const void* X, int PX, int tx0,
   const int nchunks = (npairs + 31) >> 5;
   const int ngroups = C >> 3;
   const __half2 slope2 = __float2half2_rn(slope);
+#pragma unroll 1
   for (int task = pw; task < ngroups * nchunks; task += np) {
     const int g = task / nchunks, ch = task - g * nchunks;
     const int pr = ch * 32 + lane;
@@ -211,6 +227,221 @@ __device__ __forceinline__ void pair_leaky_stage(const void* X, int PX, int tx0,
 }
 
 // ---------------------------------------------------------------------------------------------
+// waits of the roles that are idle most of the time (loaders, MMA issuer, epilogue between phases): poll with a
+// back-off, so that their try_wait loops do not take issue slots from the warps that compute (the plain polling
+// loops were 17 % of all executed instructions of a snake pair)
+// ---------------------------------------------------------------------------------------------
+// (__noinline__, loops not unrolled: one small copy each -- inlined at every wait site they were 3.5 K instructions)
+__device__ __noinline__ void pair_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    __nanosleep(128);
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  mbar_timeout();
+}
+__device__ __noinline__ void pair_wait(uint64_t* bar, uint32_t parity) {   // producers: usually already complete
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  mbar_timeout();
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue of conv2:  y = out_alpha * (acc2 + b2) + res_beta * x (+ y_old)
+// An accumulator row is one time step (thread) x 16 channels; global memory is [channel][time].  Each item
+// (128-row sub-tile, 16-channel slab; a warp owns 32 rows) is transposed through a per-warp shared-memory stage
+// ([16 channels][32 rows] fp32, row pitch 36 floats: conflict-free both ways) so that every thread then owns 8
+// consecutive time steps of 2 channels: 16-byte loads of the residual / old y and 16-byte stores instead of 2-byte ones
+// (16x fewer memory instructions), and the residual vectors of the next kD items are in flight while an item is finished
+// (the scalar version paid one L2 latency per pair of items: 15-20 K cycles per tile).
+// Tile origins are multiples of 8 rows (T_out % 8 == 0), so the 8-row groups are 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStagePitch = 36;
+constexpr int kStageFloats = 16 * kStagePitch;
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4 (&v)[1], float (&f)[8]) {   // 8 halves
+  const __half2* h = reinterpret_cast<const __half2*>(&v[0]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4 (&v)[2], float (&f)[8]) {   // 8 floats
+  f[0] = __uint_as_float(v[0].x); f[1] = __uint_as_float(v[0].y); f[2] = __uint_as_float(v[0].z); f[3] = __uint_as_float(v[0].w);
+  f[4] = __uint_as_float(v[1].x); f[5] = __uint_as_float(v[1].y); f[6] = __uint_as_float(v[1].z); f[7] = __uint_as_float(v[1].w);
+}
+
+// the 8-row group that straddles the end of the utterance (or of the tile): element by element (rare)
+template <bool XF16, bool YF16>
+__device__ __noinline__ void pair_e2_tail(const char* xsrc, char* ydst, float4 fa, float4 fb, int n, float res_beta, bool accumulate) {
+  const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll 1
+  for (int e = 0; e < n; ++e) {
+    const float xv = XF16 ? __half2float(reinterpret_cast<const __half*>(xsrc)[e]) : reinterpret_cast<const float*>(xsrc)[e];
+    float val = fmaf(res_beta, xv, f[e]);
+    if (accumulate) val += YF16 ? __half2float(reinterpret_cast<const __half*>(ydst)[e]) : reinterpret_cast<const float*>(ydst)[e];
+    if constexpr (YF16) reinterpret_cast<__half*>(ydst)[e] = f16_sat(val);
+    else reinterpret_cast<float*>(ydst)[e] = val;
+  }
+}
+
+template <bool XF16, bool YF16, bool ACC>
+__device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, int nsub, float* stg, const float* bias2_s,
+                                        uint32_t tm, int q, int lane, int slab0, int slab_step, int slabs) {
+  // items whose residual (and, for the multi-receptive-field sum, old y) vectors are in flight
+  constexpr int kD = XF16 ? (ACC ? 2 : 3) : 1;
+  constexpr int XV = XF16 ? 1 : 2, YV = YF16 ? 1 : 2;   // 16-byte vectors per 8 elements
+  constexpr int XE = XF16 ? 2 : 4, YE = YF16 ? 2 : 4;   // element sizes
+  const int nsl = (slabs - slab0 + slab_step - 1) / slab_step;
+  const int nitems = nsub * nsl;
+  const int limit = min(a.T_out, ti.len - ti.t0);   // valid output rows of this tile
+  const int c0 = lane >> 2, g = lane & 3;           // this thread's slots of an item: channels c0, c0 + 8; rows 8g .. 8g+7 of the warp's 32
+  const int r8 = q * 32 + 8 * g;
+  const char* xrow = reinterpret_cast<const char*>(a.x) + ((long long)ti.b * a.x_bs + ti.t0 + r8) * XE;
+  char* yrow = reinterpret_cast<char*>(a.y) + ((long long)ti.b * a.y_bs + ti.t0 + r8) * YE;
+  const float out_alpha = a.out_alpha, res_beta = a.res_beta;
+  constexpr bool accumulate = ACC;
+  constexpr int PV = XV + (ACC ? YV : 0);           // residual vectors, then the old y vectors
+  uint4 pre[kD][2][PV];
+  auto geom = [&](int k, int& sub, int& s) {
+    sub = k / nsl;
+    s = slab0 + (k - sub * nsl) * slab_step;
+  };
+  auto prefetch = [&](int k, uint4 (&p)[2][PV]) {
+    int sub, s;
+    geom(k, sub, s);
+    const bool full = sub * kTileM + r8 + 8 <= limit;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const char* src = xrow + ((long long)(s * 16 + c0 + 8 * i) * a.x_ld + sub * kTileM) * XE;
+#pragma unroll
+      for (int v = 0; v < XV; ++v) p[i][v] = full ? ldg128(src + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (ACC) {
+        const char* ysrc = yrow + ((long long)(s * 16 + c0 + 8 * i) * a.y_ld + sub * kTileM) * YE;
+#pragma unroll
+        for (int v = 0; v < YV; ++v)
+          p[i][XV + v] = full ? *reinterpret_cast<const uint4*>(ysrc + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  auto process = [&](int k, const uint4 (&p)[2][PV]) {
+    int sub, s;
+    geom(k, sub, s);
+    uint32_t v[16];
+    __syncwarp();                                    // the previous item's stage reads are done
+    tmem_ld_x16(tm + (uint32_t)(sub * a.C + s * 16), v);
+    float bias[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias2_s + s * 16 + 4 * i);
+      bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) stg[i * kStagePitch + lane] = fmaf(__uint_as_float(v[i]), out_alpha, bias[i]);
+    __syncwarp();
+    const int o8 = sub * kTileM + r8;
+    if (o8 >= limit) return;
+    const bool full = o8 + 8 <= limit;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int cl = c0 + 8 * i;
+      const long long crow = (long long)(s * 16 + cl);
+      char* ydst = yrow + (crow * a.y_ld + sub * kTileM) * YE;
+      float f[8];
+      {
+        const float4 s0 = *reinterpret_cast<const float4*>(stg + cl * kStagePitch + 8 * g);
+        const float4 s1 = *reinterpret_cast<const float4*>(stg + cl * kStagePitch + 8 * g + 4);
+        f[0] = s0.x; f[1] = s0.y; f[2] = s0.z; f[3] = s0.w; f[4] = s1.x; f[5] = s1.y; f[6] = s1.z; f[7] = s1.w;
+      }
+      if (full) {
+        float r[8];
+        {
+          uint4 xv[XV];
+#pragma unroll
+          for (int w = 0; w < XV; ++w) xv[w] = p[i][w];
+          unpack8(xv, r);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(res_beta, r[e], f[e]);
+        if constexpr (ACC) {   // the multi-receptive-field sum: last pair of the 2nd / 3rd residual block only
+          uint4 yv[YV];
+#pragma unroll
+          for (int w = 0; w < YV; ++w) yv[w] = p[i][XV + w];
+          float yo[8];
+          unpack8(yv, yo);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += yo[e];
+        }
+        if constexpr (YF16) {
+          *reinterpret_cast<uint4*>(ydst) = make_uint4(f16x2_sat(f[0], f[1]), f16x2_sat(f[2], f[3]), f16x2_sat(f[4], f[5]), f16x2_sat(f[6], f[7]));
+        } else {
+          *reinterpret_cast<float4*>(ydst) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(ydst + 16) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      } else {
+        pair_e2_tail<XF16, YF16>(xrow + (crow * a.x_ld + sub * kTileM) * XE, ydst, make_float4(f[0], f[1], f[2], f[3]),
+                                 make_float4(f[4], f[5], f[6], f[7]), limit - o8, res_beta, accumulate);
+      }
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kD; ++d)
+    if (d < nitems) prefetch(d, pre[d]);
+  for (int k0 = 0; k0 < nitems; k0 += kD) {
+#pragma unroll
+    for (int d = 0; d < kD; ++d) {
+      const int k = k0 + d;
+      if (k < nitems) {
+        process(k, pre[d]);
+        if (k + kD < nitems) prefetch(k + kD, pre[d]);
+      }
+    }
+  }
+}
+
+// Any other combination of stream types (fp32 residual streams: the high-precision mode and the tests): one compact
+// copy, thread = time step, element-wise global accesses (a warp reads / writes 32 consecutive time steps per channel).
+// Kept out of line so that its registers and code do not weigh on the fp16 variants.
+__device__ __noinline__ void pair_e2_generic(const PairArgs& a, const PairTile& ti, int nsub, const float* bias2_s, uint32_t tm,
+                                             int q, int lane, int slab0, int slab_step, int slabs) {
+  const int limit = min(a.T_out, ti.len - ti.t0);
+  const int XE = a.x_f16 ? 2 : 4, YE = a.y_f16 ? 2 : 4;
+#pragma unroll 1
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int o = sub * kTileM + q * 32 + lane;
+    const bool ok = o < limit;
+    const long long t = ti.t0 + (ok ? o : 0);
+#pragma unroll 1
+    for (int s = slab0; s < slabs; s += slab_step) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld_x16(tm + (uint32_t)(sub * a.C + s * 16), v);
+      tmem_ld_wait();
+      if (!ok) continue;
+      const char* xp = reinterpret_cast<const char*>(a.x) + ((long long)ti.b * a.x_bs + (long long)(s * 16) * a.x_ld + t) * XE;
+      char* yp = reinterpret_cast<char*>(a.y) + ((long long)ti.b * a.y_bs + (long long)(s * 16) * a.y_ld + t) * YE;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const float xv = a.x_f16 ? __half2float(*reinterpret_cast<const __half*>(xp)) : *reinterpret_cast<const float*>(xp);
+        float val = fmaf(a.res_beta, xv, fmaf(__uint_as_float(v[i]), a.out_alpha, bias2_s[s * 16 + i]));
+        if (a.accumulate) val += a.y_f16 ? __half2float(*reinterpret_cast<const __half*>(yp)) : *reinterpret_cast<const float*>(yp);
+        if (a.y_f16) *reinterpret_cast<__half*>(yp) = f16_sat(val);
+        else *reinterpret_cast<float*>(yp) = val;
+        xp += (long long)a.x_ld * XE;
+        yp += (long long)a.y_ld * YE;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <bool SNAKE>
@@ -228,7 +459,10 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
   uint64_t* w_empty = w_full + a.ring_slots;
   float* bias1_s = reinterpret_cast<float*>(smem + a.bias_off);
   float* bias2_s = bias1_s + a.C;                 // bias2 * out_alpha
+  float2* snake1_s = reinterpret_cast<float2*>(bias2_s + a.C);   // (e^alpha, 1/(e^beta + 1e-9)) of ACT1, ACT2
+  float2* snake2_s = snake1_s + a.C;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.tmem_off);
+  float* stage_s = reinterpret_cast<float*>(smem + a.stage_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_kernel_start = clock64();
@@ -267,6 +501,10 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
   for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
     bias1_s[i] = a.bias1 ? __ldg(a.bias1 + i) : 0.f;
     bias2_s[i] = a.bias2 ? __ldg(a.bias2 + i) * a.out_alpha : 0.f;
+    if constexpr (SNAKE) {
+      snake1_s[i] = make_float2(__expf(__ldg(a.alpha1 + i)), 1.0f / (__expf(__ldg(a.beta1 + i)) + 1e-9f));
+      snake2_s[i] = make_float2(__expf(__ldg(a.alpha2 + i)), 1.0f / (__expf(__ldg(a.beta2 + i)) + 1e-9f));
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -288,13 +526,13 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     // ================================ producers ================================
     const int pw = warp;
     auto p1 = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait_relaxed(bars + BX_FULL, j & 1);
-      mbar_wait_relaxed(bars + BA1_EMPTY, (j & 1) ^ 1);
+      pair_wait(bars + BX_FULL, j & 1);
+      pair_wait(bars + BA1_EMPTY, (j & 1) ^ 1);
       if (threadIdx.x == 0) { ptrace(a, 12, j); ptrace(a, 0, j); }
       const int ta0 = ta0_of(ti), tx0 = tx0_of(ti);
       if constexpr (SNAKE) {
-        if (a.x_f16) pair_snake_stage<true>(X, a.PX, tx0, a.alpha1, a.beta1, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
-        else pair_snake_stage<false>(X, a.PX, tx0, a.alpha1, a.beta1, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
+        if (a.x_f16) pair_snake_stage<true>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
+        else pair_snake_stage<false>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
       } else {
         if (a.x_f16) pair_leaky_stage<true>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, A1, pw, NP, lane);
         else pair_leaky_stage<false>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, A1, pw, NP, lane);
@@ -309,12 +547,12 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     };
     auto p2 = [&](const PairTile& ti, uint32_t j) {
       if constexpr (SNAKE) {
-        mbar_wait_relaxed(bars + BSCR_FULL, j & 1);
-        mbar_wait_relaxed(bars + BA2_EMPTY, (j & 1) ^ 1);
+        pair_wait(bars + BSCR_FULL, j & 1);
+        pair_wait(bars + BA2_EMPTY, (j & 1) ^ 1);
         if (threadIdx.x == 0) ptrace(a, 2, j);
         const int tu0 = tu0_of(ti);
         const int tsc0 = tu0 & ~7;               // SCR column 8 holds time tsc0
-        pair_snake_stage<true>(SCR, a.PS, tsc0 - 8, a.alpha2, a.beta2, a.C, tu0 + a.h, a.R2v, a.Rp2, ti.len, A2, pw, NP, lane);
+        pair_snake_stage<true>(SCR, a.PS, tsc0 - 8, snake2_s, a.C, tu0 + a.h, a.R2v, a.Rp2, ti.len, A2, pw, NP, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -333,13 +571,13 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     const int slabs = a.C >> 4;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     auto e1 = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait_relaxed(bars + BACC1_FULL, j & 1);
-      if constexpr (SNAKE) mbar_wait_relaxed(bars + BSCR_EMPTY, (j & 1) ^ 1);
-      else mbar_wait_relaxed(bars + BA2_EMPTY, (j & 1) ^ 1);
+      pair_wait_sleep(bars + BACC1_FULL, j & 1);
+      if constexpr (SNAKE) pair_wait_sleep(bars + BSCR_EMPTY, (j & 1) ^ 1);
+      else pair_wait_sleep(bars + BA2_EMPTY, (j & 1) ^ 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) ptrace(a, 4, j);
       const int tu0 = tu0_of(ti);
-      const int nsub = nsub1_of(ti);
+      const int nsub = (a.dbg_skip & 4) ? 0 : nsub1_of(ti);
       for (int sub = 0; sub < nsub; ++sub) {
         const int r = sub * kTileM + q * 32 + lane;     // u1 row of this thread
         for (int s = slab0; s < slabs; s += slab_step) {
@@ -353,11 +591,15 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
             bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
           }
           tmem_ld_wait();
+          const bool row_ok = r < a.NR;                  // the last sub-tile may be partial (NR is a multiple of 32)
           if constexpr (SNAKE) {
             // [channel][time] fp16 scratch for the streaming filter; column 8 <-> time tu0 & ~7
             __half* dst = SCR + (long long)(s * 16) * a.PS + (tu0 - (tu0 & ~7) + 8 + r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(long long)i * a.PS] = f16_sat(__uint_as_float(v[i]) + bias[i]);
+            for (int i = 0; i < 16; ++i) {
+              const __half hv = f16_sat(__uint_as_float(v[i]) + bias[i]);
+              if (row_ok) dst[(long long)i * a.PS] = hv;
+            }
           } else {
             const int t = tu0 + r;
             const bool valid = t >= 0 && t < ti.len;     // conv2 sees zeros outside the utterance
@@ -370,8 +612,10 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
               o[i] = valid ? f16x2_sat(f0, f1) : 0u;
             }
             __half* dst = A2 + ((long long)(2 * s) * a.Rp2 + r) * 8;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(dst + (long long)a.Rp2 * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            if (row_ok) {
+              *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(dst + (long long)a.Rp2 * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
           }
         }
       }
@@ -385,82 +629,18 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       if (ew == 0 && lane == 0) ptrace(a, 5, j);
     };
     auto e2 = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait_relaxed(bars + BACC2_FULL, j & 1);
+      pair_wait_sleep(bars + BACC2_FULL, j & 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) ptrace(a, 6, j);
-      const int nsub = nsub2_of(ti);
-      const uint32_t xb = (uint32_t)((long long)ti.b * a.x_bs), yb = (uint32_t)((long long)ti.b * a.y_bs);
-      const uint32_t x_ld = (uint32_t)a.x_ld, y_ld = (uint32_t)a.y_ld;
-      const float* xf = reinterpret_cast<const float*>(a.x);
-      const __half* xh = reinterpret_cast<const __half*>(a.x);
-      float* yf = reinterpret_cast<float*>(a.y);
-      __half* yh = reinterpret_cast<__half*>(a.y);
-      const float out_alpha = a.out_alpha, res_beta = a.res_beta;
-      // work items = (sub-tile, 16-channel slab); the residual rows of two items are requested before either is finished
-      const int nsl = (slabs - slab0 + slab_step - 1) / slab_step;
-      const int nitems = nsub * nsl;
-      auto item_geom = [&](int k, int& o, int& s) {
-        const int sub = k / nsl;
-        s = slab0 + (k - sub * nsl) * slab_step;
-        o = sub * kTileM + q * 32 + lane;
-      };
-      auto fetch = [&](int k, float (&r)[16]) {
-        int o, s;
-        item_geom(k, o, s);
-        const int t = min(ti.t0 + o, ti.len - 1);
-        uint32_t off = xb + (uint32_t)(s * 16) * x_ld + (uint32_t)t;
-        if (a.x_f16) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i, off += x_ld) r[i] = __half2float(xh[off]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i, off += x_ld) r[i] = xf[off];
-        }
-      };
-      auto finish = [&](int k, const float (&r)[16]) {
-        int o, s;
-        item_geom(k, o, s);
-        const int sub = k / nsl;
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld_x16(acc2_col + lane_base + (uint32_t)(sub * a.C + s * 16), v);
-        float val[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias2_s + s * 16 + 4 * i);
-          val[4 * i] = b4.x; val[4 * i + 1] = b4.y; val[4 * i + 2] = b4.z; val[4 * i + 3] = b4.w;
-        }
-        if (a.accumulate) {   // the multi-receptive-field sum: last pair of the 2nd / 3rd residual block only
-          uint32_t yoff = yb + (uint32_t)(s * 16) * y_ld + (uint32_t)min(ti.t0 + o, ti.len - 1);
-          if (a.y_f16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, yoff += y_ld) val[i] += __half2float(yh[yoff]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, yoff += y_ld) val[i] += yf[yoff];
-          }
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) val[i] = fmaf(res_beta, r[i], fmaf(__uint_as_float(v[i]), out_alpha, val[i]));
-        const int t = ti.t0 + o;
-        if (o < a.T_out && t < ti.len) {
-          uint32_t yoff = yb + (uint32_t)(s * 16) * y_ld + (uint32_t)t;
-          if (a.y_f16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, yoff += y_ld) yh[yoff] = f16_sat(val[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, yoff += y_ld) yf[yoff] = val[i];
-          }
-        }
-      };
-      float ra[16], rb[16];
-      for (int k = 0; k < nitems; k += 2) {
-        fetch(k, ra);
-        if (k + 1 < nitems) fetch(k + 1, rb);
-        finish(k, ra);
-        if (k + 1 < nitems) finish(k + 1, rb);
+      const uint32_t tm = acc2_col + lane_base;
+      float* stg = stage_s + ew * kStageFloats;
+      const int nsub2 = nsub2_of(ti);
+      if (a.dbg_skip & 2) {
+      } else if (a.x_f16 && a.y_f16) {   // the generators' fp16 streams: the two hot variants, inlined
+        if (a.accumulate) pair_e2<true, true, true>(a, ti, nsub2, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+        else pair_e2<true, true, false>(a, ti, nsub2, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+      } else {
+        pair_e2_generic(a, ti, nsub2, bias2_s, tm, q, lane, slab0, slab_step, slabs);
       }
       tc_fence_before();
       __syncwarp();
@@ -483,16 +663,18 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     auto conv = [&](uint32_t smA_u, int Rp, int tap_stride, int nsub, uint32_t acc_col, int chunk0, bool& first) {
       const uint32_t lbo_a = (uint32_t)Rp * 16u;
       const uint32_t a_kstep = (2u * lbo_a) >> 4;
+#pragma unroll 1
       for (int jt = 0; jt < a.K; ++jt) {
         const uint32_t a_row = smA_u + (uint32_t)(jt * tap_stride) * 16u;
+#pragma unroll 1
         for (int kc = 0; kc < a.n_kchunks; ++kc, ++cc) {
           int slot;
           if (a.resident) {
             slot = chunk0 + jt * a.n_kchunks + kc;
-            if (first) mbar_wait(w_full + slot, 0);
+            if (first) pair_wait(w_full + slot, 0);
           } else {
             slot = cc % a.ring_slots;
-            mbar_wait(w_full + slot, (cc / a.ring_slots) & 1);
+            pair_wait(w_full + slot, (cc / a.ring_slots) & 1);
           }
           __syncwarp();
           tc_fence_after();
@@ -501,7 +683,8 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
           const uint32_t fresh = (jt == 0 && kc == 0) ? 0u : 1u;
           const uint32_t a_lo0 = smem_desc_lo(a_base, lbo_a), b_lo0 = smem_desc_lo(b_base, lbo_b);
           if (elect_one()) {
-            for (int sub = 0; sub < nsub; ++sub) {
+#pragma unroll 1
+            for (int sub = 0; sub < ((a.dbg_skip & 1) ? 0 : nsub); ++sub) {
               uint32_t a_lo = a_lo0 + (uint32_t)(sub * kTileM), b_lo = b_lo0;   // 16 bytes per row -> +1 per row
               const uint32_t d_col = acc_col + (uint32_t)(sub * a.C);
               umma_ss_lohi<false>(d_col, a_lo, desc_hi, b_lo, desc_hi, idesc, fresh);
@@ -519,8 +702,8 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       first = false;
     };
     auto m1 = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait(bars + BA1_FULL, j & 1);
-      mbar_wait(bars + BACC1_EMPTY, (j & 1) ^ 1);
+      pair_wait_sleep(bars + BA1_FULL, j & 1);
+      pair_wait_sleep(bars + BACC1_EMPTY, (j & 1) ^ 1);
       __syncwarp();
       if (lane == 0) ptrace(a, 8, j);
       tc_fence_after();
@@ -533,8 +716,8 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       if (lane == 0) ptrace(a, 9, j);
     };
     auto m2 = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait(bars + BA2_FULL, j & 1);
-      mbar_wait(bars + BACC2_EMPTY, (j & 1) ^ 1);
+      pair_wait_sleep(bars + BA2_FULL, j & 1);
+      pair_wait_sleep(bars + BACC2_EMPTY, (j & 1) ^ 1);
       __syncwarp();
       if (lane == 0) ptrace(a, 10, j);
       tc_fence_after();
@@ -551,7 +734,7 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     // ================================ X loader ================================
     // one bulk copy per channel row: global [b][c][lo, hi) -> X[c][lo - tx0 ...]; lanes share the rows
     auto xl = [&](const PairTile& ti, uint32_t j) {
-      mbar_wait(bars + BX_EMPTY, (j & 1) ^ 1);
+      pair_wait_sleep(bars + BX_EMPTY, (j & 1) ^ 1);
       __syncwarp();
       const int tx0 = tx0_of(ti);
       const int ta0 = ta0_of(ti);
@@ -564,6 +747,7 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       __syncwarp();
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a.x) + ((long long)ti.b * a.x_bs + lo) * esz;
       uint8_t* dst = X + (long long)(lo - tx0) * esz;
+#pragma unroll 1
       for (int c = lane; c < a.C; c += 32)
         bulk_copy_g2s(dst + (long long)c * a.PX * esz, src + (long long)c * a.x_ld * esz, nbytes, bars + BX_FULL);
     };
@@ -576,11 +760,13 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     if (a.resident) {
       // only when this CTA has a tile to run (a CTA must not exit with bulk copies in flight)
       bool any = false;
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < a.total_tiles && !any; tile += gridDim.x) {
         PairTile ti;
         any = pair_tile(a, tile, ti);
       }
       if (any) {
+#pragma unroll 1
         for (int c = 0; c < 2 * a.n_chunks; ++c) {
           if (elect_one()) {
             const uint8_t* src = c < a.n_chunks ? w1 + (long long)c * a.chunk_bytes : w2 + (long long)(c - a.n_chunks) * a.chunk_bytes;
@@ -593,9 +779,10 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     } else {
       uint32_t cc = 0;
       auto stream = [&](const uint8_t* w) {
+#pragma unroll 1
         for (int c = 0; c < a.n_chunks; ++c, ++cc) {
           const int slot = cc % a.ring_slots;
-          mbar_wait(w_empty + slot, ((cc / a.ring_slots) & 1) ^ 1);
+          pair_wait_sleep(w_empty + slot, ((cc / a.ring_slots) & 1) ^ 1);
           __syncwarp();
           if (elect_one()) {
             mbar_arrive_expect_tx(w_full + slot, a.chunk_bytes);
@@ -625,7 +812,7 @@ struct PairDevice {
 };
 static PairDevice g_pair_dev[64];
 static long long* g_pair_trace = nullptr;
-static int g_pair_trace_on = -1, g_pair_debug = -1, g_pair_max_s = -1;
+static int g_pair_trace_on = -1, g_pair_debug = -1, g_pair_max_s = -1, g_pair_skip = 0;
 
 static int pair_device(PairDevice*& d) {
   int dev = 0;
@@ -641,6 +828,8 @@ static int pair_device(PairDevice*& d) {
     g_pair_debug = getenv("TB200_PLAN_DEBUG") != nullptr;
     const char* e = getenv("TB200_PAIR_MAX_S");
     g_pair_max_s = e ? atoi(e) : 0;
+    e = getenv("TB200_PAIR_SKIP");
+    g_pair_skip = e ? atoi(e) : 0;
   }
   return 0;
 }
@@ -662,23 +851,30 @@ static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
   a.p2 = (a.K - 1) / 2;
   a.p1 = a.p2 * a.dil;
   const int esz = a.x_f16 ? 2 : 4;
-  const int smax = g_pair_max_s > 0 ? g_pair_max_s : 8;
-  for (int S = smax; S >= 1; --S) {
-    const int NR = S * kTileM;
-    const int T_out = NR - 2 * a.h - 2 * a.p2;
+  // NR = rows of conv1 per tile: a multiple of 32 (an epilogue warp owns 32 accumulator rows), the last 128-row
+  // sub-tile at least half used; the largest that fits wins (halo recompute and the per-segment warm-up of the
+  // streaming filter are per tile).
+  const int nr_max = (g_pair_max_s > 0 ? g_pair_max_s : 8) * kTileM;
+  for (int NR = nr_max; NR >= 64; NR -= 32) {
+    if (NR % kTileM != 0 && NR % kTileM < 64) continue;
+    const int S = (NR + kTileM - 1) / kTileM;
+    const int T_out = (NR - 2 * a.h - 2 * a.p2) & ~7;   // multiple of 8: tile origins stay 16-byte aligned
     if (T_out <= 0) continue;
     if (2 * S * a.C > 512) continue;
-    if (S > 1) {
-      const int T_prev = (S - 1) * kTileM - 2 * a.h - 2 * a.p2;
+    if (NR > 64) {
+      const int T_prev = (NR - 32 - 2 * a.h - 2 * a.p2) & ~7;
       if (T_prev >= a.L_max) continue;                                             // tile longer than the data
-      if ((long long)a.B * ((a.L_max + T_out - 1) / T_out) < 2LL * sm_count) continue;   // keep every SM busy
+      if (NR > kTileM && (long long)a.B * ((a.L_max + T_out - 1) / T_out) < 2LL * sm_count) continue;   // keep every SM busy
     }
+    // operand planes: the rows a conv reads past the last written one belong to discarded output rows only; they
+    // alias the next plane / the buffer behind the tile (any finite or non-finite value is harmless there)
     const int R1 = NR + 2 * a.p1, Rp1 = plane_rows(R1);
-    const int R2v = NR - 2 * a.h, Rp2 = plane_rows(NR + a.K - 1);
+    const int R2v = NR - 2 * a.h, Rp2 = plane_rows(R2v);
     const int a1_bytes = (a.C / 8) * Rp1 * 16, a2_bytes = (a.C / 8) * Rp2 * 16;
     const int PX = round_pitch(R1 + 32, esz), x_bytes = a.C * PX * esz + 128;   // + look-ahead reads of the last row
     const int PS = snake ? round_pitch(NR + 16, 2) : 0, scr_bytes = snake ? a.C * PS * 2 + 128 : 0;
-    const int fixed = (BNUM + 2 * kPairMaxRing) * 8 + 2 * a.C * 4 + 16 + 256;
+    const int stage_bytes = (snake ? PairRoles<true>::kEpi : PairRoles<false>::kEpi) * kStageFloats * 4;
+    const int fixed = (BNUM + 2 * kPairMaxRing) * 8 + 6 * a.C * 4 + 16 + 256 + stage_bytes;
     const long long avail = (long long)smem_cap - a1_bytes - a2_bytes - x_bytes - scr_bytes - fixed;
     const long long w_total = 2LL * a.n_chunks * a.chunk_bytes;
     int resident = 0, ring = 0;
@@ -686,10 +882,13 @@ static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
       resident = 1;
       ring = 2 * a.n_chunks;
     } else {
+      // streamed weights: a chunk is consumed in a few hundred cycles and refilled from L2 in one to two thousand, so
+      // the ring must hold a few chunks and >= 24 KB (a 2-slot ring of 2 KB chunks made the K = 11, C = 32 pairs 2x
+      // slower than a smaller tile with resident weights; 3 x 8 KB at C = 64 measured as good as resident weights)
       long long slots = avail / a.chunk_bytes;
       if (slots > 16) slots = 16;
       if (slots > 2 * a.n_chunks) slots = 2 * a.n_chunks;
-      if (slots < 2) continue;
+      if (slots < 3 || slots * a.chunk_bytes < 24 * 1024) continue;
       ring = (int)slots;
     }
     a.S = S; a.NR = NR; a.T_out = T_out; a.R1 = R1; a.Rp1 = Rp1; a.R2v = R2v; a.Rp2 = Rp2; a.PX = PX; a.PS = PS;
@@ -706,8 +905,9 @@ static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
     a.scr_off = off; off += scr_bytes;
     a.w_off = off; off += ring * a.chunk_bytes;
     a.bar_off = off; off += (BNUM + 2 * ring) * 8;
-    a.bias_off = off; off += 2 * a.C * 4;
+    a.bias_off = off; off += 6 * a.C * 4;   // bias1, bias2, snake parameters of both activations
     a.tmem_off = off; off += 16;
+    a.stage_off = off; off += stage_bytes;
     a.smem_total = off;
     return 0;
   }
@@ -752,11 +952,13 @@ extern "C" int tb200_respair(const tb200_respair_params* p, void* stream_v) {
   const int unit = 16 / esz_x;
   if ((reinterpret_cast<uintptr_t>(p->x) & 15) || p->x_ld % unit || p->x_bs % unit || p->x_ld < (p->L_max + unit - 1) / unit * unit)
     return fail(TB200_E_BADARG, "respair: x must be 16-byte aligned with row pitch and batch stride multiples of %d elements", unit);
+  const int unit_y = 16 / esz_y;
+  if ((reinterpret_cast<uintptr_t>(p->y) & 15) || p->y_ld % unit_y || p->y_bs % unit_y || p->y_ld < (p->L_max + unit_y - 1) / unit_y * unit_y)
+    return fail(TB200_E_BADARG, "respair: y must be 16-byte aligned with row pitch and batch stride multiples of %d elements", unit_y);
   if (p->x == p->y) return fail(TB200_E_BADARG, "respair: in-place operation is not supported (tiles read their neighbours' halos)");
   const long long lim = 1LL << 31;
   if ((long long)p->B * p->x_bs >= lim || (long long)p->B * p->y_bs >= lim || p->x_bs < 0 || p->y_bs < 0)
     return fail(TB200_E_BADARG, "respair: tensors must be addressable with 32-bit element offsets");
-  (void)esz_y;
   PairDevice* d = nullptr;
   int rc = pair_device(d);
   if (rc) return rc;
@@ -773,6 +975,7 @@ extern "C" int tb200_respair(const tb200_respair_params* p, void* stream_v) {
   rc = plan_pair(a, snake, d->max_smem, d->sm_count);
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  a.dbg_skip = g_pair_skip;
   a.trace = nullptr;
   if (g_pair_trace_on) {
     if (!g_pair_trace) TB200_CUDA_CHECK(cudaMalloc(&g_pair_trace, kPairTraceLen * sizeof(long long)));

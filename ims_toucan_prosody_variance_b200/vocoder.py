@@ -92,11 +92,18 @@ class _GeneratorBase(torch.nn.Module):
         self._buffers_cache = {}
 
     def _pair_fused(self, channels, kernel):
-        """Which residual pairs run as one tb200_respair launch.  The 128-channel pairs keep their X tile in shared
-        memory next to two operand tiles: that fits with fp16 streams only."""
+        """Which residual pairs run as one tb200_respair launch (measured per shape on B200 at config-2 sizes,
+        profiles/r2_pair_fused_vs_two_launch.txt).  The fused kernel keeps an X tile, two operand tiles (and for
+        BigVGAN the tile between the convs) in shared memory: long kernels (K = 11: 50 halo rows per tile, weights
+        streamed from L2 per tile) and the 128-channel pairs with K >= 7 are faster as two launches."""
         if not (self.fuse_pairs and ops.ResPair.supported(channels, self.precision)):
             return False
-        return channels <= 64 or self.activation_dtype == "f16"
+        if channels == 128 and (kernel > 3 or self.activation_dtype != "f16"):
+            return False
+        snake = self._names()["act"] is not None
+        if snake:
+            return kernel <= 7 and channels != 64
+        return kernel <= 7 or channels == 64
 
     # -- workspace ---------------------------------------------------------------------------
     def _workspace(self, b, frames, dev):

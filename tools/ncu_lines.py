@@ -11,24 +11,38 @@ rep, lib, ksub = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+# the library holds one cubin per translation unit: take the one that defines the kernel.  Device functions the kernel
+# calls (__noinline__) are separate .text sections; ncu lists them after the kernel's own instructions.
 lines = []          # per instruction: (file, line, text)
-inside = False
-cur = ("?", 0)
-for ln in dis:
-    if ln.startswith("//--------------------- .text."):
-        inside = ksub in ln
+for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+    if not any(ln.startswith("//--------------------- .text.") and ksub in ln for ln in dis):
         continue
-    if not inside:
-        continue
-    m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
-    if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
-        continue
-    m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
-    if m:
-        lines.append((cur[0], cur[1], m.group(2).strip()))
+    sections, name = {}, None
+    cur = ("?", 0)
+    for ln in dis:
+        if ln.startswith("//--------------------- .text."):
+            name = ln.split(".text.", 1)[1].split()[0]
+            sections[name] = []
+            continue
+        if name is None:
+            continue
+        if ln.startswith("//--------------------- "):
+            name = None
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+        if m:
+            sections[name].append((cur[0], cur[1], m.group(2).strip()))
+    kern = [k for k in sections if ksub in k][0]
+    lines = list(sections[kern])
+    called = set(re.findall(r"\(([A-Za-z0-9_]+)\)", " ".join(t for _, _, t in lines if t.startswith("CALL") or " CALL" in t)))
+    extra = [k for k in sections if k != kern and (k in called or os.environ.get("NCU_LINES_ALL_CALLEES"))]
+    callee_sections = {k: sections[k] for k in extra}
+    break
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -36,6 +50,17 @@ hdr = rows[1]
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 body = [r for r in rows[2:] if len(r) == len(hdr)]
+if len(body) != len(lines):
+    # try appending the called device functions (every order of the few candidates is cheap to test by length only)
+    import itertools
+    for r in range(1, len(callee_sections) + 1):
+        for combo in itertools.permutations(callee_sections, r):
+            if len(lines) + sum(len(callee_sections[k]) for k in combo) == len(body):
+                for k in combo:
+                    lines += callee_sections[k]
+                break
+        if len(lines) == len(body):
+            break
 if len(body) != len(lines):
     print(f"warning: report has {len(body)} SASS lines, cubin function has {len(lines)}", file=sys.stderr)
 n = min(len(body), len(lines))
