@@ -568,10 +568,12 @@ static int launch_attention(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, co
                             int32_t out_ld, cudaStream_t s) {
   auto kern = relpos_attention_kernel<DK>;
   const int smem = (int)sizeof(AttnSmem<DK>);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured_per_dev[kMaxDeviceSlots] = {};   // per kernel instantiation (DK) and device
+  const int slot = current_device_slot();
+  if (slot < 0) return fail(TB200_E_NODEVICE, "relpos_attention: no current CUDA device");
+  if (!configured_per_dev[slot]) {
     TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured_per_dev[slot] = true;
   }
   dim3 grid((L_max + kAtQ - 1) / kAtQ, H, B);
   kern<<<grid, 256, smem, s>>>(qkv, qkv_bs, qkv_ld, pos, pos_ld, pos_center, pos_cols, bias_u, bias_v, len, H, L_max, out,

@@ -59,12 +59,14 @@ static void aa_filter_taps(float out[12]) {
 }
 
 static int ensure_constants() {
-  static bool done = false;
-  if (done) return 0;
+  static bool done[kMaxDeviceSlots] = {};   // __constant__ memory is per device
+  const int slot = current_device_slot();
+  if (slot < 0) return fail(TB200_E_NODEVICE, "no current CUDA device");
+  if (done[slot]) return 0;
   float taps[12];
   aa_filter_taps(taps);
   TB200_CUDA_CHECK(cudaMemcpyToSymbol(c_aa_filter, taps, sizeof(taps)));
-  done = true;
+  done[slot] = true;
   return 0;
 }
 

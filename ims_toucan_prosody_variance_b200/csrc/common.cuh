@@ -23,6 +23,14 @@ int fail(int code, const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// Index of the current device (per-device caches: a process may drive several GPUs), or -1.
+constexpr int kMaxDeviceSlots = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDeviceSlots) return -1;
+  return dev;
+}
+
 // ---------------------------------------------------------------------------------------------
 // anti-aliasing filter of alias_free_torch.Activation1d: kaiser_sinc_filter1d(0.25, 0.3, 12)
 // (symmetric, sums to 1).  Filled at library load (api.cu) from the closed form, in double.

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kSimtThreads) conv1d_simt_kernel(const __grid_
   const int b = blockIdx.x / tiles_t;
   const int t0 = (blockIdx.x - b * tiles_t) * kSimtTT;
   const int n0 = blockIdx.y * kSimtTN;
-  const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+  const int len = a.len_in ? min(__ldg(a.len_in + b), a.L_in_max) : a.L_in_max;   // never beyond the declared extent
   const int rows = len + (a.up > 0 ? 1 : 0);
   if (t0 >= rows || len <= 0) return;
   const int len_out = a.up > 0 ? len * a.up : len;
@@ -123,7 +123,10 @@ int conv1d_simt(const tb200_conv1d_params* p, cudaStream_t stream) {
   const int Rs = kSimtTT + a.R - kTileM;
   const int smem = (kSimtCK * Rs + kSimtCK * a.ntaps * kSimtTN + (kSimtThreads / 32) * 2 * kAaScratch) * 4;
   if (smem > 200 * 1024) return fail(TB200_E_NOSMEM, "conv1d(simt): %d bytes of shared memory", smem);
-  static int configured = 0;
+  static int configured_per_dev[kMaxDeviceSlots] = {};   // largest dynamic shared-memory limit set so far, per device
+  const int slot = current_device_slot();
+  if (slot < 0) return fail(TB200_E_NODEVICE, "conv1d(simt): no current CUDA device");
+  int& configured = configured_per_dev[slot];
   if (smem > configured) {
     TB200_CUDA_CHECK(cudaFuncSetAttribute(conv1d_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;

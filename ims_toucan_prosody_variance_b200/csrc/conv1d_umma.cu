@@ -624,6 +624,12 @@ __device__ TB200_ROLE_INLINE void epilogue_generic(const ConvArgs& a, uint32_t t
 // two smaller kernels allocate registers better than one with every path inlined.
 // CTAS = resident CTAs per SM: 2 halves the per-CTA registers (64), shared memory and TMEM columns but doubles the
 // independent warps (and scoreboards) that hide global-memory latency -- used for the pointwise staging family.
+// Valid input length of utterance b, clamped to the padded extent the caller declared (a length above L_in_max would
+// make the staging read and the epilogue write rows behind the row pitch).
+__device__ __forceinline__ int tile_len(const ConvArgs& a, int b) {
+  return a.len_in ? min(__ldg(a.len_in + b), a.L_in_max) : a.L_in_max;
+}
+
 template <typename T, bool SNAKE, int CTAS>
 __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int kWorkerWarps = Roles<SNAKE>::kWorkers, kMmaWarp = Roles<SNAKE>::kMma, kLoadWarp = Roles<SNAKE>::kLoad;
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_utt;
       const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-      const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+      const int len = tile_len(a, b);
       if (t0 >= len + extra_row || len <= 0) continue;
       const int t_lo = t0 - a.halo_l;
       // pull this CTA's NEXT tile towards L2 while the current one is staged (the tile schedule is static)
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         const int ntile = tile + gridDim.x;
         const int nb = ntile / a.tiles_per_utt;
         const int nt0 = (ntile - nb * a.tiles_per_utt) * rows_tile;
-        const int nlen = a.len_in ? __ldg(a.len_in + nb) : a.L_in_max;
+        const int nlen = tile_len(a, nb);
         if (nt0 < nlen + extra_row && nlen > 0) {
           const int esz = a.x_f16 ? 2 : 4, per_line = 128 / esz;
           const int lo = max(nt0 - a.halo_l, 0) / per_line * per_line;
@@ -764,7 +770,16 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w);
       if (a.resident) {
-        for (int c = 0; c < a.n_chunks; ++c) {
+        // A CTA whose tiles are all skipped (ragged batch) goes straight to the final barrier and exits: it must not
+        // leave bulk copies (and their complete_tx) in flight into shared memory that the SM's next CTA may own.
+        bool any = false;
+        for (int tile = blockIdx.x; tile < a.total_tiles && !any; tile += gridDim.x) {
+          const int b = tile / a.tiles_per_utt;
+          const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
+          const int len = tile_len(a, b);
+          any = !(t0 >= len + extra_row || len <= 0);
+        }
+        for (int c = 0; any && c < a.n_chunks; ++c) {
           if (elect_one()) {
             mbar_arrive_expect_tx(w_full + c, a.chunk_bytes);
             bulk_copy_g2s(smW + (long long)c * a.chunk_bytes, wsrc + (long long)c * a.chunk_bytes, a.chunk_bytes, w_full + c);
@@ -775,7 +790,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
           const int b = tile / a.tiles_per_utt;
           const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-          const int len = __shfl_sync(0xffffffffu, a.len_in ? __ldg(a.len_in + b) : a.L_in_max, 0);
+          const int len = __shfl_sync(0xffffffffu, tile_len(a, b), 0);
           if (t0 >= len + extra_row || len <= 0) continue;
           for (int nt = 0; nt < a.n_ntiles; ++nt)
             for (int pn = 0; pn < a.n_panels; ++pn)
@@ -812,7 +827,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_utt;
         const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-        const int len = __shfl_sync(0xffffffffu, a.len_in ? __ldg(a.len_in + b) : a.L_in_max, 0);
+        const int len = __shfl_sync(0xffffffffu, tile_len(a, b), 0);
         const int rows = len + extra_row;
         if (t0 >= rows || len <= 0) continue;
         const int nsub = min(a.S, (rows - t0 + kTileM - 1) / kTileM);
@@ -892,7 +907,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_utt;
       const int t0 = (tile - b * a.tiles_per_utt) * rows_tile;
-      const int len = a.len_in ? __ldg(a.len_in + b) : a.L_in_max;
+      const int len = tile_len(a, b);
       const int rows = len + extra_row;
       if (t0 >= rows || len <= 0) continue;
       const int len_out = a.up > 0 ? len * a.up : len;
@@ -903,7 +918,7 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
         const int ntile = tile + gridDim.x;
         const int nb = ntile / a.tiles_per_utt;
         const int nt0 = (ntile - nb * a.tiles_per_utt) * rows_tile;
-        const int nlen = a.len_in ? __ldg(a.len_in + nb) : a.L_in_max;
+        const int nlen = tile_len(a, nb);
         if (nt0 < nlen) {
           const int esz = a.residual ? (a.r_f16 ? 2 : 4) : (a.y_f16 ? 2 : 4);
           const char* base = a.residual ? reinterpret_cast<const char*>(a.residual) + (long long)nb * a.r_bs * esz
@@ -968,15 +983,50 @@ __global__ void __launch_bounds__(Roles<SNAKE>::kThreads, CTAS) conv1d_umma_kern
 // host launcher
 // ---------------------------------------------------------------------------------------------
 static long long* g_trace = nullptr;   // TB200_TRACE=1 only (debugging aid; the one allocation the library ever makes)
-static int g_sm_count = 0;
-static int g_max_smem = 0;
+
+// Per-device state (a process may drive several GPUs): SM count, shared-memory limit, and which kernel instantiations
+// have had their dynamic shared-memory limit raised on that device.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int sm_count = 0, max_smem = 0;
+  bool configured[4] = {false, false, false, false};
+};
+static DeviceState g_dev[kMaxDevices];
+static thread_local DeviceState* t_dev = nullptr;   // device of the call in progress
+#define g_sm_count (t_dev->sm_count)
+#define g_max_smem (t_dev->max_smem)
+
+// Tuning / debugging knobs: read from the environment ONCE per process (not per launch).
+struct Knobs {
+  bool init = false;
+  bool snake_plan_old = false, trace = false, l2_prefetch = false, plan_debug = false;
+  double snake_a2_ratio = 0.3;
+  int max_s = 0, nprod_snake = 0, nprod_pw = 0;
+};
+static Knobs g_knobs;
+static void read_knobs() {
+  if (g_knobs.init) return;
+  g_knobs.snake_plan_old = getenv("TB200_SNAKE_PLAN_OLD") != nullptr;
+  if (const char* e = getenv("TB200_SNAKE_A2_RATIO")) g_knobs.snake_a2_ratio = atof(e);
+  g_knobs.trace = getenv("TB200_TRACE") != nullptr;
+  if (const char* e = getenv("TB200_L2_PREFETCH")) g_knobs.l2_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("TB200_MAX_S")) g_knobs.max_s = atoi(e);
+  if (const char* e = getenv("TB200_NPROD_SNAKE")) g_knobs.nprod_snake = atoi(e);
+  if (const char* e = getenv("TB200_NPROD_PW")) g_knobs.nprod_pw = atoi(e);
+  g_knobs.plan_debug = getenv("TB200_PLAN_DEBUG") != nullptr;
+  g_knobs.init = true;
+}
 
 static int device_props() {
-  if (g_sm_count) return 0;
   int dev = 0;
   TB200_CUDA_CHECK(cudaGetDevice(&dev));
-  TB200_CUDA_CHECK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  TB200_CUDA_CHECK(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(TB200_E_BADARG, "conv1d: device index %d", dev);
+  t_dev = &g_dev[dev];
+  if (!t_dev->sm_count) {
+    TB200_CUDA_CHECK(cudaDeviceGetAttribute(&t_dev->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    TB200_CUDA_CHECK(cudaDeviceGetAttribute(&t_dev->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  read_knobs();
   return 0;
 }
 
@@ -985,7 +1035,7 @@ int fill_conv_args(const tb200_conv1d_params* p, int precision, ConvArgs& a);  /
 template <typename T, bool SNAKE, int CTAS>
 static int launch_t(const ConvArgs& a, int smem_bytes, cudaStream_t stream) {
   auto kern = conv1d_umma_kernel<T, SNAKE, CTAS>;
-  static bool configured = false;
+  bool& configured = t_dev->configured[(sizeof(T) == 2 ? 0 : 2) + (SNAKE ? 1 : 0)];
   if (!configured) {
     TB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem / CTAS));
     configured = true;
@@ -1065,7 +1115,7 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
             // (MMA issue has since dropped to 12 K cycles; the rule fires from 30 % of the staging time).
             // (A full cost model over every (S, buffers, panels) was tried and lost on the C >= 128 layers, whose
             // weight re-streaming per tile it underestimates.)
-            if (tall_first && a_bufs == 1 && S > 1 && getenv("TB200_SNAKE_PLAN_OLD") == nullptr) {
+            if (tall_first && a_bufs == 1 && S > 1 && !g_knobs.snake_plan_old) {
               const int n_prod = Roles<true>::kWorkers - 8;
               const int ncb = a.Cin_pad / 32;
               int g = ncb > 0 ? ncb : 1, r2 = n_prod;
@@ -1075,8 +1125,7 @@ static int plan(ConvArgs& a, int elem_bytes, int rows_max, int ctas, bool tall_f
               const double mma = (double)S * a.ntaps * (a.Cin_pad / 16) * (a.NT > 70 ? a.NT : 70);
               const long long budget2 = (long long)smem_cap - fixed - 2LL * a_bytes;
               const long long slots = budget2 > 0 ? budget2 / c.chunk_bytes : 0;
-              double ratio = 0.3;
-              if (const char* e = getenv("TB200_SNAKE_A2_RATIO")) ratio = atof(e);   // tuning knob
+              const double ratio = g_knobs.snake_a2_ratio;   // tuning knob
               if (mma >= ratio * stage && slots >= 4) {
                 c.a_bufs = 2;
                 c.resident = 0;
@@ -1153,15 +1202,15 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   a.n_prod = snake ? Roles<true>::kWorkers - 8
                    : Roles<false>::kWorkers - ((a.residual || a.accumulate || !(a.epi_fast || a.epi_up)) ? 8 : 4);
   a.trace = nullptr;
-  if (getenv("TB200_TRACE")) {
+  if (g_knobs.trace) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceLen * sizeof(long long)));
     TB200_CUDA_CHECK(cudaMemsetAsync(g_trace, 0, kTraceLen * sizeof(long long), stream));
     a.trace = g_trace;
   }
   a.l2_prefetch = 0;  // measured: next-tile L2 prefetch doubles DRAM reads (lines evicted before use) -- kept as a knob
-  if (const char* e = getenv("TB200_L2_PREFETCH")) a.l2_prefetch = atoi(e) != 0;
-  if (const char* e = getenv("TB200_MAX_S")) {  // tuning knob: cap the sub-tiles per CTA tile
-    const int cap = atoi(e);
+  a.l2_prefetch = g_knobs.l2_prefetch;
+  if (g_knobs.max_s >= 1) {  // tuning knob: cap the sub-tiles per CTA tile
+    const int cap = g_knobs.max_s;
     if (cap >= 1 && a.S > cap) {
       ConvArgs t = a;
       // re-plan with a smaller S by shrinking rows_max-independent fields
@@ -1177,13 +1226,12 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
       a = t;
     }
   }
-  if (const char* e = getenv(a.act == TB200_ACT_AA_SNAKEBETA ? "TB200_NPROD_SNAKE" : "TB200_NPROD_PW")) {  // tuning knob
-    const int v = atoi(e);
+  if (const int v = (a.act == TB200_ACT_AA_SNAKEBETA ? g_knobs.nprod_snake : g_knobs.nprod_pw)) {  // tuning knob
     const int w = a.act == TB200_ACT_AA_SNAKEBETA ? Roles<true>::kWorkers : Roles<false>::kWorkers;
     if (v >= 2 && v <= kMaxProdWarps && (w - v == 4 || w - v == 8)) a.n_prod = v;
   }
   const int smem_bytes = ws_layout(a).total;
-  if (getenv("TB200_PLAN_DEBUG"))
+  if (g_knobs.plan_debug)
     fprintf(stderr, "tb200 plan: Cin=%d Cout=%d taps=%d up=%d act=%d L=%d -> S=%d a_bufs=%d acc_bufs=%d panels=%d ntiles=%d %s ring=%d n_prod=%d smem=%d\n",
             a.Cin, a.Cout, a.ntaps, a.up, a.act, p->L_in_max, a.S, a.a_bufs, a.acc_bufs, a.n_panels, a.n_ntiles,
             a.resident ? "resident" : "streamed", a.ring_slots, a.n_prod, smem_bytes);

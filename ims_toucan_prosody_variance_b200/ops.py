@@ -28,6 +28,29 @@ def _dtype_code(t):
     raise _lib.EngineError(f"unsupported activation dtype {t.dtype}")
 
 
+def _on_device(fn):
+    """Run an ABI wrapper on the device its tensors live on: the kernels launch on the CURRENT device and stream, so a
+    model on cuda:1 called while cuda:0 is current would otherwise launch on GPU 0 with GPU-1 pointers.  All tensor
+    arguments must share one device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            for t in (a if isinstance(a, (tuple, list)) else (a,)):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    if dev is None:
+                        dev = t.device
+                    elif t.device != dev:
+                        raise _lib.EngineError(f"toucan_b200: tensors on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -40,6 +63,7 @@ class ConvLayer:
     weight: torch layout, fp32 -- (C_out, C_in, K), or (C_in, C_out, 2u) when transposed_stride=u.
     """
 
+    @_on_device
     def __init__(self, weight, bias=None, dilation=1, padding=0, transposed_stride=0, precision="f16"):
         lib = _lib.load()
         _require_cuda(weight, bias)
@@ -63,6 +87,7 @@ class ConvLayer:
     def out_len(self, length):
         return length * self.up if self.up else length
 
+    @_on_device
     def __call__(self, x, lengths, out, l_in_max=None, act=ACT_NONE, slope=0.0, alpha=None, beta=None, out_act=OUT_NONE,
                  out_alpha=1.0, residual=None, res_beta=1.0, accumulate=False):
         """x (B,C_in,L) -> out (B,C_out,L_out), both NCL with contiguous rows.  lengths: int32 (B) or None."""
@@ -116,6 +141,7 @@ class ResPair:
     def supported(channels, precision):
         return precision in ("f16", PREC_F16) and channels in (32, 64, 128)
 
+    @_on_device
     def __call__(self, x, lengths, out, l_max=None, slope=0.1, out_alpha=1.0, res_beta=1.0, accumulate=False):
         """x (B,C,L) -> out (B,C,L), NCL with contiguous rows, fp32 or fp16; out must not alias x."""
         global LAUNCHES
@@ -146,6 +172,7 @@ class ResPair:
         return out
 
 
+@_on_device
 def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1.0, duration_scale=1.0, t_ld=None):
     """text (B,T,62) fp32, text_len (B) int32, log_dur (B,T_ld) fp32 or gold_dur (B,T_ld) int64 (T_ld >= T, row pitch).
     Returns durations (B,T_ld) int64, inclusive prefix sums (B,T_ld) int32, frames (B) int32."""
@@ -167,6 +194,7 @@ def duration_finalize(text, text_len, log_dur=None, gold_dur=None, pause_scale=1
     return dur, cum, frames
 
 
+@_on_device
 def variance_edit(curve, text, text_len, which, variance_scale=1.0, t_ld=None):
     """In-place pitch (which=0) / energy (which=1) edits + variance scaling on curve (B,T_ld) fp32."""
     global LAUNCHES
@@ -180,6 +208,7 @@ def variance_edit(curve, text, text_len, which, variance_scale=1.0, t_ld=None):
     return curve
 
 
+@_on_device
 def length_regulate(enc, cum, text_len, frames, f_max, pitch=None, energy=None, wp=None, bp=None, we=None, be=None,
                     out=None, want_index=False):
     """enc (B,C,T) NCL fp32 -> (B,C,F_max) NCL fp32 (only f < frames[b] written)."""
@@ -214,6 +243,7 @@ def _call(name, *args):
     LAUNCHES += 1
 
 
+@_on_device
 def channel_norm(x, lengths, out, gamma, beta, l_max, conditional=False, eps=1e-12):
     """LayerNorm over channels (conditional=False) or ConditionalLayerNorm with per-utterance (B,C) gamma/beta."""
     _require_cuda(x, out, gamma, beta, lengths)
@@ -224,6 +254,7 @@ def channel_norm(x, lengths, out, gamma, beta, l_max, conditional=False, eps=1e-
     return out
 
 
+@_on_device
 def group_norm(x, lengths, out, gamma, beta, groups, l_max, residual=None, tanh=False, eps=1e-5):
     _require_cuda(x, out, gamma, beta, lengths, residual)
     b, c, _ = x.shape
@@ -233,6 +264,7 @@ def group_norm(x, lengths, out, gamma, beta, groups, l_max, residual=None, tanh=
     return out
 
 
+@_on_device
 def glu_dwconv(x, lengths, out, w, bias, bn_mean, bn_var, bn_gamma, bn_beta, l_max, bn_eps=1e-5):
     _require_cuda(x, out, w, bias, lengths)
     b, c, _ = out.shape
@@ -241,6 +273,7 @@ def glu_dwconv(x, lengths, out, w, bias, bn_mean, bn_var, bn_gamma, bn_beta, l_m
     return out
 
 
+@_on_device
 def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max):
     _require_cuda(qkv, out, pos, bias_u, bias_v, lengths)
     b, c3, _ = qkv.shape
@@ -250,6 +283,7 @@ def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, 
     return out
 
 
+@_on_device
 def rowvec_affine(x, lengths, out, l_max, vec=None, scale=1.0):
     _require_cuda(x, out, vec, lengths)
     b, c, _ = out.shape
@@ -259,6 +293,7 @@ def rowvec_affine(x, lengths, out, l_max, vec=None, scale=1.0):
     return out
 
 
+@_on_device
 def to_ncl(x_blc, lengths, out, l_max):
     """(B,L,C) -> NCL (B,C,L)."""
     _require_cuda(x_blc, out, lengths)
@@ -267,6 +302,7 @@ def to_ncl(x_blc, lengths, out, l_max):
     return out
 
 
+@_on_device
 def from_ncl(x, lengths, out_blc, l_max):
     """NCL (B,C,L) -> (B,L,C)."""
     _require_cuda(x, out_blc, lengths)
@@ -275,6 +311,7 @@ def from_ncl(x, lengths, out_blc, l_max):
     return out_blc
 
 
+@_on_device
 def squeeze2(x, lengths, out, l_max, inverse=False):
     """Glow squeeze (inverse=False: lengths/l_max unsqueezed) or unsqueeze (inverse=True: lengths/l_max squeezed).
     The channel count passed to the kernel is always the UNSQUEEZED one."""
@@ -285,6 +322,7 @@ def squeeze2(x, lengths, out, l_max, inverse=False):
     return out
 
 
+@_on_device
 def wn_gate(a, lengths, out, l_max):
     _require_cuda(a, out, lengths)
     b, h, _ = out.shape
@@ -292,6 +330,7 @@ def wn_gate(a, lengths, out, l_max):
     return out
 
 
+@_on_device
 def flow_close(x, ml, lengths, l_max, w_inv, an_bias, an_logs):
     _require_cuda(x, ml, lengths, w_inv, an_bias, an_logs)
     b, c, _ = x.shape
@@ -299,6 +338,7 @@ def flow_close(x, ml, lengths, l_max, w_inv, an_bias, an_logs):
     return x
 
 
+@_on_device
 def l2_normalize(x):
     _require_cuda(x)
     x = x.contiguous().float()
@@ -307,6 +347,7 @@ def l2_normalize(x):
     return y
 
 
+@_on_device
 def cln_mlp(e, w0, b0, w2, b2, w4, b4):
     """e (B,E); stacked MLP weights (N,...) -> (N,B,Cc)."""
     _require_cuda(e, w0, b0, w2, b2, w4, b4)

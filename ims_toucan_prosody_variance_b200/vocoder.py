@@ -98,7 +98,9 @@ class _GeneratorBase(torch.nn.Module):
         streamed from L2 per tile) and the 128-channel pairs with K >= 7 are faster as two launches."""
         if not (self.fuse_pairs and ops.ResPair.supported(channels, self.precision)):
             return False
-        if channels == 128 and (kernel > 3 or self.activation_dtype != "f16"):
+        if self.activation_dtype != "f16":   # fp32 streams double the X tile: smaller tiles, no gain over two launches
+            return False
+        if channels == 128 and kernel > 3:
             return False
         snake = self._names()["act"] is not None
         if snake:

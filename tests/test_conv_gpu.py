@@ -13,7 +13,7 @@ TOL = {"fp32": 2e-5, "tf32": 2e-3, "f16": 2e-3}
 
 def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0, snake=False, residual=False,
          out_act=0, out_alpha=1.0, res_beta=1.0, accumulate=False, x_half=False, y_half=False, seed=0,
-         y_misalign=False):
+         y_misalign=False, alpha_scale=0.3):
     from ims_toucan_prosody_variance_b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, Cin, L, generator=g)
@@ -22,7 +22,7 @@ def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0,
     wshape = (Cin, Cout, 2 * up) if up else (Cout, Cin, K)
     w = torch.randn(wshape, generator=g) / (Cin * (2 if up else K)) ** 0.5
     bias = torch.randn(Cout, generator=g) * 0.1
-    alpha = torch.randn(Cin, generator=g) * 0.3
+    alpha = torch.randn(Cin, generator=g) * alpha_scale
     beta = torch.randn(Cin, generator=g) * 0.3
     Lout = L * up if up else L
     res = torch.randn(B, Cout, Lout, generator=g) if residual else None
@@ -111,6 +111,13 @@ def test_aa_snake_prologue(cuda, prec):
     _run(cuda, prec, B=2, Cin=32, Cout=32, K=3, dil=3, L=300, lens=[300, 45], snake=True, residual=True)
 
 
+def test_aa_snake_trained_scale_alpha(cuda):
+    """Trained BigVGAN checkpoints reach |alpha| of 2-3 (log scale): sin arguments of tens of radians.  The staging
+    uses sin.approx (range reduction in fp32, absolute error growing with |x e^alpha|): still within the f16 tolerance."""
+    _run(cuda, "f16", B=2, Cin=32, Cout=32, K=3, dil=1, L=300, lens=[300, 64], snake=True, alpha_scale=1.5, seed=4)
+    _run(cuda, "f16", B=1, Cin=64, Cout=64, K=7, dil=3, L=600, snake=True, alpha_scale=1.5, x_half=True, seed=5)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_epilogue_variants(cuda, prec):
     _run(cuda, prec, B=2, Cin=32, Cout=16, K=7, dil=1, L=260, lens=[260, 129], act=1, slope=0.01, out_act=1)
@@ -195,3 +202,11 @@ def test_transposed_unaligned_output_rows(cuda, u, y_half):
 
 def test_transposed_with_residual_keeps_generic_epilogue(cuda):
     _run(cuda, "f16", B=2, Cin=64, Cout=32, K=8, dil=1, L=150, lens=[150, 40], up=4, residual=True, res_beta=0.5)
+
+
+def test_ragged_ctas_without_valid_tiles_then_relaunch(cuda):
+    """Resident weights + a ragged batch in which whole CTAs own only skipped tiles (they must not leave bulk copies in
+    flight when they exit), followed by more launches on the same SMs."""
+    lens = [2000] + [3] * 200 + [2000]
+    for seed in range(3):
+        _run(cuda, "f16", B=len(lens), Cin=32, Cout=32, K=3, dil=1, L=2000, lens=lens, act=1, slope=0.1, residual=True, seed=seed)

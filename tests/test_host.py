@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     from ims_toucan_prosody_variance_b200 import _lib
     header = open(os.path.join(ROOT, "include", "toucan_b200.h")).read()
     declared = set(re.findall(r"\b(tb200_[a-z0-9_]+)\s*\(", header))
-    declared -= {"tb200_conv1d_params"}
+    declared -= {"tb200_conv1d_params", "tb200_respair_params"}
     assert declared, "no declarations parsed"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
@@ -37,19 +37,28 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().tb200_version() == int(re.search(r"#define TB200_VERSION (\d+)", header).group(1))
 
 
-def test_params_struct_matches_header():
+@pytest.mark.parametrize("struct,cls", [("tb200_conv1d_params", "Conv1dParams"), ("tb200_respair_params", "RespairParams")])
+def test_params_struct_matches_header(struct, cls):
+    """Field names, order and C types of the ctypes mirrors equal the structs of include/toucan_b200.h."""
     from ims_toucan_prosody_variance_b200 import _lib
     header = open(os.path.join(ROOT, "include", "toucan_b200.h")).read()
-    body = header[header.index("typedef struct tb200_conv1d_params {"):header.index("} tb200_conv1d_params;")]
+    body = header[header.index("typedef struct %s {" % struct):header.index("} %s;" % struct)]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = []
+    fields = []
     for stmt in body.split("{", 1)[1].split(";"):
         stmt = stmt.strip()
         if not stmt:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int32_t|int64_t)\s*\*?", "", stmt)
-        names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
-    assert names == [f[0] for f in _lib.Conv1dParams._fields_]
+        m = re.match(r"^(const\s+)?(void|float|int32_t|int64_t)\s*(.*)$", stmt)
+        base = m.group(2)
+        for n in m.group(3).split(","):
+            n = n.strip()
+            ptr = n.startswith("*")
+            fields.append((n.lstrip("*").strip(), "ptr" if ptr else base))
+    ctype = {"ptr": ctypes.c_void_p, "float": ctypes.c_float, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64}
+    mirror = getattr(_lib, cls)._fields_
+    assert [f[0] for f in mirror] == [f[0] for f in fields]
+    assert [f[1] for f in mirror] == [ctype[f[1]] for f in fields]
 
 
 def test_module_state_dict_roundtrip(tmp_path):

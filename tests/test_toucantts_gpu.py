@@ -166,6 +166,65 @@ def test_long_form_external_prosody(cuda):
     assert torch.isfinite(mel).all()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_config3_length_mel_parity(cuda, prec):
+    """BASELINE.json configs[2] at its longest utterance: 200 phonemes -> ~1 000 frames.  The decoder's attention then
+    runs 16 key tiles per query tile and the k = 31 depthwise conv sees full-length rows; mel rel-L1 <= 1e-3 against the
+    oracle on the same flow noise, durations bit-exact (fp32) / frame count equal."""
+    from oracle import factory, restate
+    model, fsd = _engine(cuda, prec)
+    n_ph, seed = 200, 21
+    text = factory.make_phoneme_tensor(n_ph, seed)
+    emb = factory.make_utterance_embedding(seed)
+    with torch.inference_mode():
+        ref = restate.toucantts_forward(fsd, text, emb, lang_id=12, generator=torch.Generator().manual_seed(7))
+    frames = int(ref["durations"].sum())
+    assert frames >= 800
+    noise = torch.randn((1, 80, frames), generator=torch.Generator().manual_seed(7))
+    r = model.synthesize_batch(text.unsqueeze(0).to(cuda), torch.tensor([n_ph]), utterance_embedding=emb.unsqueeze(0).to(cuda),
+                               lang_ids=torch.tensor([12]), noise=noise)
+    torch.cuda.synchronize()
+    flips = int((r["durations"][0, :n_ph].cpu() != ref["durations"]).sum())
+    _log([f"== config-3 length, {prec}: {n_ph} phonemes, {frames} frames, duration flips {flips}"])
+    if prec == "fp32":
+        assert flips == 0
+    if flips == 0:
+        mel = r["mel_ncl"][0, :, :2 * (frames // 2)].t().cpu()
+        err = _rel_l1(mel, ref["mel"])
+        _log([f"   mel rel-L1 {err:.3e}"])
+        assert err <= MEL_TOL[prec]
+    else:   # tf32 encoder feeding the fp32 duration head: a log-duration on a .5 boundary may flip by one frame
+        assert flips <= 2 and abs(int(r["frames"][0]) - frames) <= 2
+
+
+def test_long_form_1000_phonemes_mel_parity(cuda):
+    """Config-5 shaped input: 1 000 phonemes with external durations / pitch / energy (UtteranceCloner override path,
+    InferenceToucanTTS.py:204-212) -> ~3 000 frames; the mel itself is checked against the oracle (fp32 mode), not
+    only durations and finiteness.  The relative positional table is regrown past its initial 256 positions."""
+    from oracle import factory, restate
+    model, fsd = _engine(cuda, "fp32")
+    n_ph = 1000
+    text = factory.make_phoneme_tensor(n_ph, 31)
+    emb = factory.make_utterance_embedding(31)
+    d, p, e = factory.make_gold_prosody(text, 31)
+    d = d.clamp(max=4)
+    with torch.inference_mode():
+        ref = restate.toucantts_forward(fsd, text, emb, lang_id=12, durations=d.clone(), pitch=p.clone(), energy=e.clone(),
+                                        generator=torch.Generator().manual_seed(3))
+    frames = int(ref["durations"].sum())
+    assert frames >= 2000
+    noise = torch.randn((1, 80, frames), generator=torch.Generator().manual_seed(3))
+    r = model.synthesize_batch(text.unsqueeze(0).to(cuda), torch.tensor([n_ph]), utterance_embedding=emb.unsqueeze(0).to(cuda),
+                               lang_ids=torch.tensor([12]), gold_durations=d.unsqueeze(0).to(cuda),
+                               gold_pitch=p.reshape(1, -1, 1).to(cuda), gold_energy=e.reshape(1, -1, 1).to(cuda), noise=noise)
+    torch.cuda.synchronize()
+    assert torch.equal(r["durations"][0, :n_ph].cpu(), ref["durations"])
+    mel = r["mel_ncl"][0, :, :2 * (frames // 2)].t().cpu()
+    err = _rel_l1(mel, ref["mel"])
+    _log([f"== long form: {n_ph} phonemes, {frames} frames, mel rel-L1 {err:.3e}"])
+    assert err <= 1e-3
+
+
 def test_all_zero_durations_rescue_and_tiny_utterance(cuda):
     """LengthRegulator.py:52-53: an utterance whose durations sum to 0 gets one frame per phoneme; a 3-phoneme
     utterance (shorter than every conv kernel) still goes through the whole path."""

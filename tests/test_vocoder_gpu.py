@@ -112,6 +112,31 @@ def test_full_size_batch_is_batch_invariant(cuda, tmp_path, kind):
     assert restate.snr_db(got, ref) >= 40.0
 
 
+@pytest.mark.parametrize("streams", ["f32", "f16"])
+@pytest.mark.parametrize("kind", ["bigvgan", "hifigan"])
+def test_full_500_frame_utterance_vs_oracle(cuda, tmp_path, kind, streams):
+    """One complete 500-frame utterance of the BASELINE.json configs[1] batch (64 x 500) against the oracle, in both
+    residual-stream modes (f16 = the benchmarked configuration: fused residual pairs): waveform SNR >= 40 dB over all
+    192 000 samples, so every tile position and every tile boundary of the full-size launch is covered."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory, restate
+    sd = factory.make_state_dict(kind, 1234)
+    path = os.path.join(tmp_path, f"{kind}_{streams}.pt")
+    torch.save({"generator": sd}, path)
+    cls = tb.HiFiGANGenerator if kind == "hifigan" else tb.BigVGAN
+    model = cls(path, precision="f16", activation_dtype=streams).to(cuda)
+    model.remove_weight_norm()
+    mel = factory.make_mel(64, 500, seed=100)
+    wave = model.forward_batch(mel.to(cuda), torch.full((64,), 500, dtype=torch.int32, device=cuda))
+    b = 41
+    fwd = restate.hifigan_forward if kind == "hifigan" else restate.bigvgan_forward
+    with torch.inference_mode():
+        ref = fwd(restate.fold_weight_norm(sd), mel[b])
+    snr = restate.snr_db(wave[b].cpu(), ref)
+    print(f"{kind} streams {streams}: utterance {b} of the 64 x 500 batch, SNR vs oracle {snr:.1f} dB")
+    assert wave.shape == (64, 500 * 384) and snr >= 40.0
+
+
 @pytest.mark.parametrize("kind", ["hifigan", "bigvgan"])
 def test_fp16_residual_stream_mode(cuda, tmp_path, kind):
     """activation_dtype="f16": the residual stream is stored as fp16 in HBM (looser-precision mode, stated separately:
