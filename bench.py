@@ -318,6 +318,69 @@ def run_tts_workload(args, rank, local_rank, world, dev, dist):
     print(json.dumps(line))
 
 
+def run_config4(args, rank, world, dev, dist):
+    """BASELINE.json configs[3]: ONE global batch of 512 ragged utterances (20..200 phonemes), partitioned by utterance
+    over the ranks with sharding.partition_lpt (longest-processing-time first on the estimated cost), each rank running
+    text -> wave through TextToWave (length buckets of <= 64 utterances) with no collective on the data path; the ranks
+    then exchange output lengths and timings.  Strong scaling: the total work is fixed as N grows.  Returns the extra
+    `config4` object of the bench line (on every rank; rank 0 prints it)."""
+    import random
+
+    import ims_toucan_prosody_variance_b200 as tb
+    from ims_toucan_prosody_variance_b200 import sharding
+    from oracle import factory
+    n_total = args.config4_utterances
+    rng = random.Random(4)
+    lens = [rng.randint(20, 200) for _ in range(n_total)]
+    shards = sharding.partition_lpt([sharding.estimate_cost(n) for n in lens], world)
+    mine = shards[rank]
+    tts = tb.ToucanTTS(weights=factory.make_state_dict("toucantts", 1234), precision=args.acoustic_precision).to(dev)
+    tts.store_inverse_all()
+    voc, _ = build_generator(args.vocoder, args.precision, dev, args.activations)
+    eng = tb.TextToWave(tts, voc)
+    texts = [factory.make_phoneme_tensor(lens[i], 5000 + i) for i in mine]
+    emb = torch.stack([factory.make_utterance_embedding(i) for i in mine]) if mine else torch.zeros((0, 64))
+    lang = torch.full((len(mine),), 12, dtype=torch.int64)
+
+    def one_pass():
+        return eng.synthesize(texts, emb, lang_ids=lang, noise="device", device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    waves = one_pass()                      # warm-up (workspaces, planner caches)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    ev0.record()
+    for _ in range(reps):
+        waves = one_pass()
+    ev1.record()
+    barrier()
+    my_ms = ev0.elapsed_time(ev1) / reps
+    wlen = [int(w.numel()) for w in waves]
+    audio = sum(wlen) / SAMPLE_RATE
+    all_len = sharding.gather_output_lengths(mine, wlen, n_total, device=dev)
+    times = torch.zeros(world, dtype=torch.float64, device=dev)
+    times[rank] = my_ms
+    audios = torch.zeros(world, dtype=torch.float64, device=dev)
+    audios[rank] = audio
+    if dist is not None:
+        dist.all_reduce(times)
+        dist.all_reduce(audios)
+    t_max, t_mean = float(times.max()), float(times.mean())
+    total_audio = float(audios.sum())
+    assert int((all_len > 0).sum()) == n_total and abs(float(all_len.sum()) / SAMPLE_RATE - total_audio) < 1e-6 * total_audio + 1e-3
+    return {"workload": f"text->wave, ONE global batch of {n_total} ragged utterances (20..200 phonemes) partitioned by utterance "
+                        f"(LPT on estimated cost) over {world} GPU(s), ToucanTTS ({args.acoustic_precision}) + {args.vocoder}",
+            "scaling": "strong", "utterances": n_total, "audio_s": round(total_audio, 2), "ms": round(t_max, 3),
+            "value": round(total_audio / (t_max / 1e3), 2), "unit": UNIT, "rank_ms_max": round(t_max, 3),
+            "rank_ms_mean": round(t_mean, 3), "imbalance": round(t_max / t_mean - 1.0, 4),
+            "rank_audio_s": [round(float(v), 1) for v in audios.tolist()]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +396,8 @@ def main():
     ap.add_argument("--activations", default="f16", choices=["f32", "f16"],
                     help="storage type of the vocoder residual stream in HBM (f16: fused residual pairs; f32: every conv its own launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra sharded 512-utterance text->wave run")
+    ap.add_argument("--config4-utterances", type=int, default=512)
     args = ap.parse_args()
     args.batch_given = args.batch is not None
     if args.batch is None:
@@ -435,6 +500,13 @@ def main():
     finite = bool(torch.isfinite(wave).all()) and float(wave.abs().max()) <= 1.0
     if not finite:
         raise SystemExit("bench.py: generator produced non-finite or out-of-range samples")
+    # ---- extra (after the headline numbers are taken): configs[3], one global batch sharded by utterance ----
+    config4 = None
+    if not args.no_config4:
+        del wave
+        model._buffers_cache = {}
+        torch.cuda.empty_cache()
+        config4 = run_config4(args, rank, world, dev, dist)
 
     if rank != 0:
         if dist is not None:
@@ -474,6 +546,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "vocoder_rtf": round((ms_step / 1e3) / audio_s_per_step, 8),
+        "config4": config4,
     }
     print(json.dumps(line))
     if dist is not None:

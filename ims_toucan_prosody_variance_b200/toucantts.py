@@ -101,7 +101,9 @@ class ToucanTTS(torch.nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise EngineError("toucan_b200 ToucanTTS runs on CUDA only: call .to('cuda') before store_inverse_all()/forward()")
-        sd = layouts.fold_weight_norm({k: v.detach() for k, v in self.state_dict().items()})
+        # folded on the host (load time; a few hundred small tensors), so that the only device work of loading a model is
+        # the packing kernels of this library and plain copies
+        sd = {k: v.to(dev) for k, v in layouts.fold_weight_norm({k: v.detach().cpu() for k, v in self.state_dict().items()}).items()}
         prec = self.precision
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         cache = {}
@@ -182,9 +184,10 @@ class ToucanTTS(torch.nn.Module):
             fl = _Block()
             fl.an_bias, fl.an_logs = f32(sd[an + "bias"]).reshape(-1), f32(sd[an + "logs"]).reshape(-1)
             # Glow.py:130-139: W = P (L*mask + I)(U*mask^T + diag(sign_s*exp(log_s))), cached fp32 inverse
-            l = sd[ic + "l"] * sd[ic + "l_mask"] + sd[ic + "eye"]
-            u = sd[ic + "u"] * sd[ic + "l_mask"].transpose(0, 1).contiguous() + torch.diag(sd[ic + "sign_s"] * torch.exp(sd[ic + "log_s"]))
-            fl.w_inv = torch.inverse(torch.matmul(sd[ic + "p"], torch.matmul(l, u)).float().cpu()).to(dev).contiguous()
+            ich = {k: sd[ic + k].float().cpu() for k in ("l", "l_mask", "eye", "u", "sign_s", "log_s", "p")}   # 4x4: on the host
+            l = ich["l"] * ich["l_mask"] + ich["eye"]
+            u = ich["u"] * ich["l_mask"].transpose(0, 1).contiguous() + torch.diag(ich["sign_s"] * torch.exp(ich["log_s"]))
+            fl.w_inv = torch.inverse(torch.matmul(ich["p"], torch.matmul(l, u))).to(dev).contiguous()
             fl.start = conv(cp + "start.weight", cp + "start.bias")
             fl.end = conv(cp + "end.weight", cp + "end.bias")
             fl.cond = conv(cp + "wn.cond_layer.weight", cp + "wn.cond_layer.bias")

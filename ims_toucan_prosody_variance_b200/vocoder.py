@@ -58,7 +58,9 @@ class _GeneratorBase(torch.nn.Module):
         if dev.type != "cuda":
             raise ops._lib.EngineError("toucan_b200 generators run on CUDA only: call .to('cuda') before "
                                        "remove_weight_norm()/forward()")
-        sd = layouts.fold_weight_norm({k: v.detach() for k, v in self.state_dict().items()})
+        # folded on the host (load time; a few hundred small tensors), so that the only device work of loading a model is
+        # the packing kernels of this library and plain copies
+        sd = {k: v.to(dev) for k, v in layouts.fold_weight_norm({k: v.detach().cpu() for k, v in self.state_dict().items()}).items()}
         n = self._names()
         prec = self.precision
         pk = {}
