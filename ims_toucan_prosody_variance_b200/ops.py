@@ -274,11 +274,12 @@ def glu_dwconv(x, lengths, out, w, bias, bn_mean, bn_var, bn_gamma, bn_beta, l_m
 
 
 @_on_device
-def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max):
+def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max, tensor_core=False):
+    """tensor_core: tcgen05 flash attention with fp16 operands (tf32 / f16 precision modes); else the fp32 CUDA-core kernel."""
     _require_cuda(qkv, out, pos, bias_u, bias_v, lengths)
     b, c3, _ = qkv.shape
     dk = c3 // 3 // heads
-    _call("tb200_relpos_attention", *_ncl(qkv), _ptr(pos), pos.stride(0), int(pos_center), pos.shape[1], _ptr(bias_u),
+    _call("tb200_relpos_attention_tc" if tensor_core else "tb200_relpos_attention", *_ncl(qkv), _ptr(pos), pos.stride(0), int(pos_center), pos.shape[1], _ptr(bias_u),
           _ptr(bias_v), _ptr(lengths), b, int(heads), dk, int(l_max), *_ncl(out))
     return out
 

@@ -252,7 +252,8 @@ class ToucanTTS(torch.nn.Module):
         ops.channel_norm(x, lens, n, *blk.norms["norm_mha"], l_max)
         blk.qkv(n, lens, qkv, l_in_max=l_max)
         pos, cap = self._positions(blk, l_max, x.device)
-        ops.relpos_attention(qkv, lens, ctx, pos, cap - 1, blk.bias_u, blk.bias_v, self.attention_heads, l_max)
+        ops.relpos_attention(qkv, lens, ctx, pos, cap - 1, blk.bias_u, blk.bias_v, self.attention_heads, l_max,
+                             tensor_core=self.precision != "fp32")
         blk.out(ctx, lens, x, l_in_max=l_max, residual=x)
         # x += ConvModule(LN(x))
         ops.channel_norm(x, lens, n, *blk.norms["norm_conv"], l_max)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TB200_VERSION 102
+#define TB200_VERSION 103
 
 enum {
   TB200_OK = 0,
@@ -259,6 +259,16 @@ int tb200_relpos_attention(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, con
                            int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v,
                            const int32_t* len, int32_t B, int32_t H, int32_t dk, int32_t L_max,
                            float* out, int64_t out_bs, int32_t out_ld, void* stream);
+
+/* The same contraction on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM): QK^T, the
+ * relative-position band (Q + v) P^T and softmax x V are 128 x 128 / 128 x 256 / 128 x dk MMA tiles per (utterance,
+ * head, 128 queries); the skewed read of the band (rel_shift, Attention.py:138-157) goes through a per-row window in
+ * shared memory.  Operands are rounded to fp16 (tf32's mantissa): used by the tf32 / f16 precision modes, the fp32
+ * mode keeps tb200_relpos_attention.  Same arguments.                                                           */
+int tb200_relpos_attention_tc(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const float* pos, int32_t pos_ld,
+                              int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v,
+                              const int32_t* len, int32_t B, int32_t H, int32_t dk, int32_t L_max,
+                              float* out, int64_t out_bs, int32_t out_ld, void* stream);
 
 /* y[b][c][t] = (x[b][c][t] + vec[b][c]) * scale; x or vec may be NULL (treated as 0).  Covers the
  * language-embedding add and the sqrt(adim) scale of RelPositionalEncoding (Conformer.py:108-118,

@@ -54,8 +54,11 @@ def _attention_reference(q, k, v, p, bu, bv):
     return torch.matmul(attn, v)                                      # (H,T,dk)
 
 
-@pytest.mark.parametrize("lens", [[1], [63], [64], [65], [1000, 17, 129], [4097]])
-def test_relpos_attention(cuda, lens):
+@pytest.mark.parametrize("tensor_core", [False, True])
+@pytest.mark.parametrize("lens", [[1], [63], [64], [65], [127, 128, 129], [1000, 17, 129], [4097]])
+def test_relpos_attention(cuda, lens, tensor_core):
+    """tensor_core=False: the fp32 CUDA-core kernel (tolerance 5e-5); True: tcgen05 flash attention with fp16 operands
+    (Q, K, the positional band, the probabilities and V are rounded to 11 bits: tolerance 4e-3 of the output scale)."""
     from ims_toucan_prosody_variance_b200 import ops
     heads, dk = 4, 48
     d = heads * dk
@@ -72,7 +75,7 @@ def test_relpos_attention(cuda, lens):
     pos_d = torch.zeros(d, _pad4(2 * cap - 1), device=cuda)
     pos_d[:, :2 * cap - 1] = pos.to(cuda)
     lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
-    ops.relpos_attention(qkv_d, lt, out_d, pos_d, cap - 1, bu.to(cuda), bv.to(cuda), heads, l_max)
+    ops.relpos_attention(qkv_d, lt, out_d, pos_d, cap - 1, bu.to(cuda), bv.to(cuda), heads, l_max, tensor_core=tensor_core)
     torch.cuda.synchronize()
     got = out_d.cpu()
     for i, t in enumerate(lens):
@@ -82,7 +85,7 @@ def test_relpos_attention(cuda, lens):
         p = pos[:, cols].reshape(heads, dk, 2 * t - 1).transpose(1, 2).double()
         ref = _attention_reference(q, k, v, p, bu.double(), bv.double())        # (H,T,dk)
         ref = ref.transpose(1, 2).reshape(d, t).float()
-        _close(got[i, :, :t], ref, 5e-5, f"attention T={t}")
+        _close(got[i, :, :t], ref, 4e-3 if tensor_core else 5e-5, f"attention T={t} tensor_core={tensor_core}")
         assert torch.all(got[i, :, t:l_max] == 7.0), "rows past the utterance's length were written"
 
 
