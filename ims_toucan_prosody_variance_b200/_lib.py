@@ -68,7 +68,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "tb200_relpos_attention": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
-    "tb200_relpos_attention_tc": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+    "tb200_relpos_attention_tc": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                           c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "tb200_rowvec_affine": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_int64, c_float, c_void_p]),

@@ -16,8 +16,10 @@
 // store address, uniform register index) and reads it back in key order.  Online softmax in registers: the thread
 // keeps its row's running max, sum and the dk output values; PV of each tile is read back from TMEM and accumulated
 // with the usual exp(m_old - m_new) rescale -- no TMEM read-modify-write.
-// Warps: 0-3 softmax (TMEM lane quarters), 4 MMA issuer, 5-7 loaders (global fp32 -> fp16 operand tiles, K/V/Pband
-// double buffered).
+// Warps: 0-3 softmax (TMEM lane quarters), 4 MMA issuer (also requests the positional band: it is pre-packed per
+// layer as fp16 operand rows [head][d/8][relative position][8], so a tile's band is one contiguous bulk copy per
+// 16-byte group -- cp.async.bulk, no conversion), 5-11 loaders (global fp32 Q/K/V -> fp16 operand tiles, several
+// tasks' loads in flight per thread; K/V/band double buffered).
 #include <cstdio>
 #include <cstdlib>
 
@@ -29,7 +31,7 @@ constexpr int kAtM = 128;          // query rows per CTA
 constexpr int kAtN = 128;          // keys per tile
 constexpr int kAtBand = 256;       // relative positions per tile
 constexpr int kAtScrPitch = kAtN * 2 + 16;   // bytes per scratch row (fp16 window + 16: conflict-free 16-byte reads)
-constexpr int kAtLoaders = 3;      // loader warps
+constexpr int kAtLoaders = 7;      // loader warps
 constexpr int kAtThreads = (4 + 1 + kAtLoaders) * 32;
 
 template <int DK>
@@ -66,8 +68,8 @@ __device__ __noinline__ void at_wait(uint64_t* bar, uint32_t parity) {
 
 template <int DK>
 __global__ void __launch_bounds__(kAtThreads, 1)
-relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, int qkv_ld, const float* __restrict__ pos, int pos_ld,
-                             int pos_center, int pos_cols, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
+relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, int qkv_ld, const __half* __restrict__ pos16, int pos_rows,
+                             int pos_center, const float* __restrict__ bias_u, const float* __restrict__ bias_v,
                              const int* __restrict__ len_ptr, int H, int L_max, float* __restrict__ out, long long out_bs, int out_ld) {
   using Lay = AtLayout<DK>;
   constexpr int kPlanes = Lay::kPlanes;
@@ -83,13 +85,13 @@ relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, in
   const float* qb = qkv + (long long)b * qkv_bs + (long long)(h * DK) * qkv_ld;
   const float* kb = qb + (long long)D * qkv_ld;
   const float* vb = kb + (long long)D * qkv_ld;
-  const float* pb = pos + (long long)(h * DK) * pos_ld;
+  const __half* pb16 = pos16 + (long long)h * kPlanes * pos_rows * 8;   // [d/8][pos_rows][8]
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(bars + AQ_FULL, kAtLoaders);
-      mbar_init(bars + AKV_FULL0, kAtLoaders);
-      mbar_init(bars + AKV_FULL1, kAtLoaders);
+      mbar_init(bars + AKV_FULL0, kAtLoaders + 1);   // + the band's bulk copies (expect_tx arrival of the MMA warp)
+      mbar_init(bars + AKV_FULL1, kAtLoaders + 1);
       mbar_init(bars + AKV_EMPTY0, 1);
       mbar_init(bars + AKV_EMPTY1, 1);
       mbar_init(bars + ASG_FULL, 1);
@@ -220,6 +222,23 @@ relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, in
     const uint32_t idesc_s = make_instr_desc(kAtN, false), idesc_g = make_instr_desc(kAtBand, false), idesc_pv = make_instr_desc(DK, false);
     const uint32_t qu = smem_u32(smem + Lay::qu_off), qv = smem_u32(smem + Lay::qv_off), pt = smem_u32(smem + Lay::p_off);
     constexpr uint32_t lbo_q = kAtM * 16, lbo_k = kAtN * 16, lbo_pb = kAtBand * 16, lbo_p = kAtM * 16, lbo_v = DK * 16;
+    // positional band of tile kt: relative positions (i0 - j0 - 127) + n, n < 256 -> rows of the packed table
+    auto request_band = [&](int kt) {
+      const int buf = kt & 1;
+      at_wait(bars + AKV_EMPTY0 + buf, ((kt >> 1) & 1) ^ 1);
+      __syncwarp();
+      if (elect_one()) {
+        const int row0 = pos_center + (i0 - kt * kAtN - 127);
+        mbar_arrive_expect_tx(bars + AKV_FULL0 + buf, Lay::pb_bytes);
+#pragma unroll
+        for (int g = 0; g < kPlanes; ++g)
+          bulk_copy_g2s(smem + Lay::pb_off + buf * Lay::pb_bytes + g * (kAtBand * 16), pb16 + ((long long)g * pos_rows + row0) * 8,
+                        kAtBand * 16, bars + AKV_FULL0 + buf);
+      }
+      __syncwarp();
+    };
+    request_band(0);
+    if (nkt > 1) request_band(1);
     at_wait(bars + AQ_FULL, 0);
     for (int kt = 0; kt < nkt; ++kt) {
       const int buf = kt & 1;
@@ -254,6 +273,7 @@ relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, in
         umma_commit(bars + AKV_EMPTY0 + buf);
       }
       __syncwarp();
+      if (kt + 2 < nkt) request_band(kt + 2);   // the buffer is free once the commit above lands
     }
   } else {
     // ================================ loaders: global fp32 -> fp16 operand tiles ================================
@@ -282,35 +302,43 @@ relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, in
       const int buf = kt & 1, j0 = kt * kAtN;
       at_wait(bars + AKV_EMPTY0 + buf, ((kt >> 1) & 1) ^ 1);
       uint8_t* ktile = smem + Lay::k_off + buf * Lay::k_bytes;
-      uint8_t* pband = smem + Lay::pb_off + buf * Lay::pb_bytes;
       uint8_t* vtile = smem + Lay::v_off + buf * Lay::v_bytes;
-      // K: [d/8][key][8]   (zero rows behind the utterance: their scores are masked, but 0 x garbage must stay finite)
-      for (int task = lt; task < kPlanes * kAtN; task += nlt) {
-        const int g = task / kAtN, r = task - g * kAtN;
-        const int kj = j0 + r;
-        float f[8];
+      // K: [d/8][key][8] (zero rows behind the utterance: their scores are masked, but 0 x garbage must stay finite)
+      // V: [key/8][d][8].  Task t < nK: K group (g, key); else V group (key/8, d).  kU tasks' loads are in flight at once.
+      constexpr int nK = kPlanes * kAtN, nV = (kAtN / 8) * DK, kU = 4;
+      for (int t0 = lt; t0 < nK + nV; t0 += kU * nlt) {
+        float f[kU][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = kj < len ? __ldg(kb + (long long)(g * 8 + e) * qkv_ld + kj) : 0.f;
-        *reinterpret_cast<uint4*>(ktile + (g * kAtN + r) * 16) = pack8(f);
-      }
-      // relative positions r = (i0 - j0 - 127) + n  <->  table column pos_center - r
-      const int r_min = i0 - j0 - 127;
-      for (int task = lt; task < kPlanes * kAtBand; task += nlt) {
-        const int g = task / kAtBand, n = task - g * kAtBand;
-        const int col = pos_center - (r_min + n);
-        float f[8];
+        for (int u = 0; u < kU; ++u) {
+          const int task = t0 + u * nlt;
+          if (task < nK) {
+            const int g = task / kAtN, r = task - g * kAtN;
+            const int kj = j0 + r;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = (col >= 0 && col < pos_cols) ? __ldg(pb + (long long)(g * 8 + e) * pos_ld + col) : 0.f;
-        *reinterpret_cast<uint4*>(pband + (g * kAtBand + n) * 16) = pack8(f);
-      }
-      // V: [key/8][d][8]
-      for (int task = lt; task < (kAtN / 8) * DK; task += nlt) {
-        const int kp = task / DK, d = task - kp * DK;
-        const int kj = j0 + kp * 8;
-        float f[8];
+            for (int e = 0; e < 8; ++e) f[u][e] = kj < len ? __ldg(kb + (long long)(g * 8 + e) * qkv_ld + kj) : 0.f;
+          } else if (task < nK + nV) {
+            const int tv = task - nK;
+            const int kp = tv / DK, d = tv - kp * DK;
+            const int kj = j0 + kp * 8;
+            if (kj + 8 <= len) {       // rows are 16-byte aligned (qkv_ld % 4 == 0, kj % 8 == 0)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(vb + (long long)d * qkv_ld + kj));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(vb + (long long)d * qkv_ld + kj + 4));
+              f[u][0] = a0.x; f[u][1] = a0.y; f[u][2] = a0.z; f[u][3] = a0.w; f[u][4] = a1.x; f[u][5] = a1.y; f[u][6] = a1.z; f[u][7] = a1.w;
+            } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = kj + e < len ? __ldg(vb + (long long)d * qkv_ld + kj + e) : 0.f;
-        *reinterpret_cast<uint4*>(vtile + (kp * DK + d) * 16) = pack8(f);
+              for (int e = 0; e < 8; ++e) f[u][e] = kj + e < len ? __ldg(vb + (long long)d * qkv_ld + kj + e) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int task = t0 + u * nlt;
+          if (task < nK) {
+            *reinterpret_cast<uint4*>(ktile + task * 16) = pack8(f[u]);           // (g * 128 + r) == task
+          } else if (task < nK + nV) {
+            *reinterpret_cast<uint4*>(vtile + (task - nK) * 16) = pack8(f[u]);    // (kp * DK + d) == task - nK
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -323,8 +351,8 @@ relpos_attention_umma_kernel(const float* __restrict__ qkv, long long qkv_bs, in
 }
 
 template <int DK>
-static int launch_attention_umma(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const float* pos, int32_t pos_ld,
-                                 int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v, const int32_t* len,
+static int launch_attention_umma(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const __half* pos16, int32_t pos_rows,
+                                 int32_t pos_center, const float* bias_u, const float* bias_v, const int32_t* len,
                                  int32_t B, int32_t H, int32_t L_max, float* out, int64_t out_bs, int32_t out_ld, cudaStream_t s) {
   auto kern = relpos_attention_umma_kernel<DK>;
   static bool configured_per_dev[kMaxDeviceSlots] = {};
@@ -335,7 +363,7 @@ static int launch_attention_umma(const float* qkv, int64_t qkv_bs, int32_t qkv_l
     configured_per_dev[slot] = true;
   }
   dim3 grid((L_max + kAtM - 1) / kAtM, H, B);
-  kern<<<grid, kAtThreads, AtLayout<DK>::total, s>>>(qkv, qkv_bs, qkv_ld, pos, pos_ld, pos_center, pos_cols, bias_u, bias_v, len, H, L_max,
+  kern<<<grid, kAtThreads, AtLayout<DK>::total, s>>>(qkv, qkv_bs, qkv_ld, pos16, pos_rows, pos_center, bias_u, bias_v, len, H, L_max,
                                                      out, out_bs, out_ld);
   TB200_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -345,20 +373,24 @@ static int launch_attention_umma(const float* qkv, int64_t qkv_bs, int32_t qkv_l
 
 using namespace tb200;
 
-extern "C" int tb200_relpos_attention_tc(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const float* pos, int32_t pos_ld,
-                                         int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v,
-                                         const int32_t* len, int32_t B, int32_t H, int32_t dk, int32_t L_max, float* out,
-                                         int64_t out_bs, int32_t out_ld, void* stream) {
-  if (!qkv || !pos || !bias_u || !bias_v || !out) return fail(TB200_E_BADARG, "relpos_attention_tc: null pointer");
+extern "C" int tb200_relpos_attention_tc(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const void* pos16, int32_t pos_rows,
+                                         int32_t pos_center, const float* bias_u, const float* bias_v, const int32_t* len,
+                                         int32_t B, int32_t H, int32_t dk, int32_t L_max, float* out, int64_t out_bs,
+                                         int32_t out_ld, void* stream) {
+  if (!qkv || !pos16 || !bias_u || !bias_v || !out) return fail(TB200_E_BADARG, "relpos_attention_tc: null pointer");
   if (B <= 0 || H <= 0 || L_max <= 0 || B > 65535 || H > 65535) return fail(TB200_E_BADARG, "relpos_attention_tc: bad shape");
-  if (pos_center - (L_max - 1) < 0 || pos_center + (L_max - 1) >= pos_cols)
-    return fail(TB200_E_BADARG, "relpos_attention_tc: positional table (%d columns, centre %d) too short for L=%d", pos_cols,
+  // every tile's 256-row band must lie inside the packed table: relative positions -(L_max+254) .. L_max+127
+  if (pos_center - (L_max + 254) < 0 || pos_center + (L_max + 127) >= pos_rows)
+    return fail(TB200_E_BADARG, "relpos_attention_tc: packed positional table (%d rows, centre %d) too short for L=%d", pos_rows,
                 pos_center, L_max);
+  if ((reinterpret_cast<uintptr_t>(pos16) & 15) || qkv_ld % 4 || qkv_bs % 4 || (reinterpret_cast<uintptr_t>(qkv) & 15))
+    return fail(TB200_E_BADARG, "relpos_attention_tc: qkv rows and the packed table must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __half* p16 = reinterpret_cast<const __half*>(pos16);
   switch (dk) {
-    case 32: return launch_attention_umma<32>(qkv, qkv_bs, qkv_ld, pos, pos_ld, pos_center, pos_cols, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
-    case 48: return launch_attention_umma<48>(qkv, qkv_bs, qkv_ld, pos, pos_ld, pos_center, pos_cols, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
-    case 64: return launch_attention_umma<64>(qkv, qkv_bs, qkv_ld, pos, pos_ld, pos_center, pos_cols, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
+    case 32: return launch_attention_umma<32>(qkv, qkv_bs, qkv_ld, p16, pos_rows, pos_center, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
+    case 48: return launch_attention_umma<48>(qkv, qkv_bs, qkv_ld, p16, pos_rows, pos_center, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
+    case 64: return launch_attention_umma<64>(qkv, qkv_bs, qkv_ld, p16, pos_rows, pos_center, bias_u, bias_v, len, B, H, L_max, out, out_bs, out_ld, s);
     default: return fail(TB200_E_BADARG, "relpos_attention_tc: head size %d not in {32,48,64}", dk);
   }
 }

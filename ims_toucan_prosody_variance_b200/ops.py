@@ -274,13 +274,40 @@ def glu_dwconv(x, lengths, out, w, bias, bn_mean, bn_var, bn_gamma, bn_beta, l_m
 
 
 @_on_device
-def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max, tensor_core=False):
-    """tensor_core: tcgen05 flash attention with fp16 operands (tf32 / f16 precision modes); else the fp32 CUDA-core kernel."""
+def relpos_attention(qkv, lengths, out, pos, pos_center, bias_u, bias_v, heads, l_max):
+    """fp32 CUDA-core kernel.  pos (D, cols): column (pos_center - r) holds relative position r."""
     _require_cuda(qkv, out, pos, bias_u, bias_v, lengths)
     b, c3, _ = qkv.shape
     dk = c3 // 3 // heads
-    _call("tb200_relpos_attention_tc" if tensor_core else "tb200_relpos_attention", *_ncl(qkv), _ptr(pos), pos.stride(0), int(pos_center), pos.shape[1], _ptr(bias_u),
+    _call("tb200_relpos_attention", *_ncl(qkv), _ptr(pos), pos.stride(0), int(pos_center), pos.shape[1], _ptr(bias_u),
           _ptr(bias_v), _ptr(lengths), b, int(heads), dk, int(l_max), *_ncl(out))
+    return out
+
+
+ATTN_BAND_PAD = 256   # zero rows on both sides of the packed positional table (a tile reads a 256-row band)
+
+
+def pack_relpos_table(pos, pos_center, heads):
+    """(D, cols) fp32 table with column (pos_center - r) = relative position r  ->  the fp16 operand rows of
+    tb200_relpos_attention_tc: (H, dk/8, rows, 8), row (center + r) = relative position r, ATTN_BAND_PAD zero rows on
+    both sides.  Returns (packed, center).  Done once per layer and table size (plain tensor ops, load time)."""
+    d, cols = pos.shape
+    dk = d // heads
+    r_lo, r_hi = pos_center - (cols - 1), pos_center            # relative positions covered: r_lo .. r_hi
+    inc = torch.flip(pos[:, :cols], dims=[1])                   # column i <-> r = r_lo + i
+    packed = torch.zeros((heads, dk // 8, cols + 2 * ATTN_BAND_PAD, 8), dtype=torch.float16, device=pos.device)
+    packed[:, :, ATTN_BAND_PAD:ATTN_BAND_PAD + cols] = inc.reshape(heads, dk // 8, 8, cols).permute(0, 1, 3, 2).to(torch.float16)
+    return packed.contiguous(), ATTN_BAND_PAD - r_lo
+
+
+@_on_device
+def relpos_attention_tc(qkv, lengths, out, pos16, pos_center, bias_u, bias_v, heads, l_max):
+    """tcgen05 flash attention with fp16 operands (tf32 / f16 precision modes).  pos16, pos_center from pack_relpos_table."""
+    _require_cuda(qkv, out, pos16, bias_u, bias_v, lengths)
+    b, c3, _ = qkv.shape
+    dk = c3 // 3 // heads
+    _call("tb200_relpos_attention_tc", *_ncl(qkv), _ptr(pos16), pos16.shape[2], int(pos_center), _ptr(bias_u), _ptr(bias_v),
+          _ptr(lengths), b, int(heads), dk, int(l_max), *_ncl(out))
     return out
 
 

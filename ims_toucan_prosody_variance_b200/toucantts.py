@@ -234,6 +234,8 @@ class ToucanTTS(torch.nn.Module):
         out = torch.zeros((1, self.attention_dimension, pe.shape[2]), dtype=torch.float32, device=dev)
         blk.pos(pe, None, out, l_in_max=2 * cap - 1)
         blk.pos_table = (out[0], cap)
+        if self.precision != "fp32":   # operand rows of the tensor-core attention, packed once per layer and table size
+            blk.pos16 = ops.pack_relpos_table(out[0][:, :2 * cap - 1], cap - 1, self.attention_heads)
         return blk.pos_table
 
     # ------------------------------------------------------------------------------------------
@@ -252,8 +254,10 @@ class ToucanTTS(torch.nn.Module):
         ops.channel_norm(x, lens, n, *blk.norms["norm_mha"], l_max)
         blk.qkv(n, lens, qkv, l_in_max=l_max)
         pos, cap = self._positions(blk, l_max, x.device)
-        ops.relpos_attention(qkv, lens, ctx, pos, cap - 1, blk.bias_u, blk.bias_v, self.attention_heads, l_max,
-                             tensor_core=self.precision != "fp32")
+        if self.precision != "fp32":
+            ops.relpos_attention_tc(qkv, lens, ctx, blk.pos16[0], blk.pos16[1], blk.bias_u, blk.bias_v, self.attention_heads, l_max)
+        else:
+            ops.relpos_attention(qkv, lens, ctx, pos, cap - 1, blk.bias_u, blk.bias_v, self.attention_heads, l_max)
         blk.out(ctx, lens, x, l_in_max=l_max, residual=x)
         # x += ConvModule(LN(x))
         ops.channel_norm(x, lens, n, *blk.norms["norm_conv"], l_max)

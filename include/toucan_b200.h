@@ -264,9 +264,12 @@ int tb200_relpos_attention(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, con
  * relative-position band (Q + v) P^T and softmax x V are 128 x 128 / 128 x 256 / 128 x dk MMA tiles per (utterance,
  * head, 128 queries); the skewed read of the band (rel_shift, Attention.py:138-157) goes through a per-row window in
  * shared memory.  Operands are rounded to fp16 (tf32's mantissa): used by the tf32 / f16 precision modes, the fp32
- * mode keeps tb200_relpos_attention.  Same arguments.                                                           */
-int tb200_relpos_attention_tc(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const float* pos, int32_t pos_ld,
-                              int32_t pos_center, int32_t pos_cols, const float* bias_u, const float* bias_v,
+ * mode keeps tb200_relpos_attention.
+ * pos16: the projected positional table packed once per layer as fp16 operand rows [H][dk/8][pos_rows][8]
+ * (16 bytes per (head, d-group, relative position)); row (pos_center + r) is relative position r, rows outside the
+ * table's own range are zero; pos_rows must cover r in [-(L_max+254), L_max+127].  qkv rows 16-byte aligned.     */
+int tb200_relpos_attention_tc(const float* qkv, int64_t qkv_bs, int32_t qkv_ld, const void* pos16, int32_t pos_rows,
+                              int32_t pos_center, const float* bias_u, const float* bias_v,
                               const int32_t* len, int32_t B, int32_t H, int32_t dk, int32_t L_max,
                               float* out, int64_t out_bs, int32_t out_ld, void* stream);
 

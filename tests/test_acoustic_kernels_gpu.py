@@ -75,7 +75,11 @@ def test_relpos_attention(cuda, lens, tensor_core):
     pos_d = torch.zeros(d, _pad4(2 * cap - 1), device=cuda)
     pos_d[:, :2 * cap - 1] = pos.to(cuda)
     lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
-    ops.relpos_attention(qkv_d, lt, out_d, pos_d, cap - 1, bu.to(cuda), bv.to(cuda), heads, l_max, tensor_core=tensor_core)
+    if tensor_core:
+        pos16, center = ops.pack_relpos_table(pos_d[:, :2 * cap - 1], cap - 1, heads)
+        ops.relpos_attention_tc(qkv_d, lt, out_d, pos16, center, bu.to(cuda), bv.to(cuda), heads, l_max)
+    else:
+        ops.relpos_attention(qkv_d, lt, out_d, pos_d, cap - 1, bu.to(cuda), bv.to(cuda), heads, l_max)
     torch.cuda.synchronize()
     got = out_d.cpu()
     for i, t in enumerate(lens):
