@@ -471,6 +471,15 @@ def bigvgan_forward(sd, mel, taps=None):
 # -----------------------------------------------------------------------------------------
 
 
+def float2pcm(sig):
+    """Utility/utils.py:20-33 (dtype int16): (sig * 32768).clip(-32768, 32767) truncated toward zero by astype."""
+    import numpy as np
+    sig = np.asarray(sig)
+    if sig.dtype.kind != "f":
+        raise TypeError("'sig' must be a float array")
+    return (sig * 32768.0 + 0).clip(-32768, 32767).astype(np.int16)
+
+
 def rel_l1(a, b):
     """mean |a-b| / mean |b| (north_star: mel relative L1 <= 1e-3 in the fp32-accumulate mode)."""
     return float((a.double() - b.double()).abs().mean() / b.double().abs().mean().clamp_min(1e-30))

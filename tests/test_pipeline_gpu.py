@@ -88,6 +88,36 @@ def test_interface_forward_batch_and_read_to_file(cuda, tmp_path):
         assert f.getframerate() == 48000 and f.getsampwidth() == 2 and f.getnframes() == 2 * wav.numel()
 
 
+def test_read_to_file_content_parity(cuda, tmp_path):
+    """read_to_file (ToucanTTSInterface.py:231-285): the file holds 10 600 samples of silence, then each non-empty
+    sentence followed by silence; in increased-compatibility mode every sample twice as 16-bit PCM at 48 kHz
+    (float2pcm, utils.py:20-33).  The written samples are compared bit for bit with the oracle's float2pcm of the
+    same waveforms (same flow-noise seed), not only by their count."""
+    import wave as wavmod
+
+    import numpy as np
+
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import restate
+    tpath, vpath, _, _ = _models(cuda, tmp_path)
+    tts = tb.ToucanTTSInterface(device="cuda", tts_model_path=tpath, vocoder_model_path=vpath, faster_vocoder=True,
+                                language="en", text2phone=_Frontend())
+    texts = ["12:3", "", "20:4", "9:1"]
+    torch.manual_seed(11)
+    waves = tts.forward_batch([t for t in texts if t.strip()])
+    out = os.path.join(tmp_path, "content.wav")
+    torch.manual_seed(11)
+    wav = tts.read_to_file(texts, out, silent=True, increased_compatibility_mode=True).cpu()
+    silence = torch.zeros(10600)
+    expect = torch.cat([silence] + [p for w in waves for p in (w.reshape(-1).cpu(), silence)])
+    assert torch.equal(wav, expect)
+    with wavmod.open(out, "rb") as f:
+        assert f.getframerate() == 48000 and f.getsampwidth() == 2 and f.getnchannels() == 1
+        pcm = np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16)
+    ref = restate.float2pcm(np.repeat(expect.numpy(), 2))
+    assert pcm.shape == ref.shape and np.array_equal(pcm, ref)
+
+
 def test_cloner_override_path(cuda, tmp_path):
     import ims_toucan_prosody_variance_b200 as tb
     from oracle import factory
