@@ -49,6 +49,7 @@ SIGNATURES = {
     "tb200_last_error": (ctypes.c_char_p, []),
     "tb200_sm_count": (c_int, []),
     "tb200_conv1d": (c_int, [ctypes.POINTER(Conv1dParams), c_void_p]),
+    "tb200_conv1d_staged": (c_int, [ctypes.POINTER(Conv1dParams), c_void_p]),
     "tb200_respair": (c_int, [ctypes.POINTER(RespairParams), c_void_p]),
     "tb200_respair_trace_read": (c_int, [c_void_p, c_int]),
     "tb200_packed_weight_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),

@@ -49,6 +49,11 @@ struct PairArgs {
   int x_f16, y_f16;
   float slope, out_alpha, res_beta;
   int accumulate;
+  // residual of the output epilogue: x itself for a pair; any (B, C, L) tensor or none for a single staged conv
+  const void* res;
+  long long r_bs;
+  int r_ld, r_f16;
+  int single;             // 1: ONE convolution (conv1 only) through the same TMA-fed pipeline, operand tiles double buffered
   // tile geometry
   int S, NR, h, p1, p2, T_out;
   int R1, Rp1;            // A1 rows used / plane pitch (rows)
@@ -58,15 +63,24 @@ struct PairArgs {
   int resident, ring_slots;
   int tiles_per_utt, total_tiles;
   int tmem_cols;
+  int x_buf_bytes, x_bufs;   // bytes of one X buffer; 1 or 2 buffers (2: single mode only)
   int a1_off, a2_off, x_off, scr_off, w_off, bar_off, bias_off, tmem_off, stage_off, smem_total;
   long long* trace;
   int dbg_skip;           // TB200_PAIR_SKIP (profiling only): 1 no MMAs, 2 no conv2 epilogue body, 4 no conv1 epilogue body
 };
 
+// Producer warps of the snake variant (the rest of the 12 worker warps run the epilogues).  The streaming filter is
+// bound by the FMA pipe, which one warp per scheduler nearly saturates (tools/snake_rate.cu: 4 warps 0.45-0.49 cycles
+// per element per SM, 8 warps 0.39-0.44).  Measured: the fused pair (two snake stages per tile) is 5-15 % faster with
+// 8 + 4 at K >= 7; the single-conv mode (one snake stage, epilogue with residual loads) is 8 % faster with 4 + 8; the
+// whole BigVGAN step is the same within noise (75.3-75.6 ms).  Default: 8 + 4.
+#ifndef TB200_PAIR_NP_SNAKE
+#define TB200_PAIR_NP_SNAKE 8
+#endif
 template <bool SNAKE>
 struct PairRoles {
-  static constexpr int kProd = SNAKE ? 8 : 4;   // 15 warps either way: up to 128 registers per thread
-  static constexpr int kEpi = SNAKE ? 4 : 8;
+  static constexpr int kProd = TB200_PAIR_NP_SNAKE > 0 && SNAKE ? TB200_PAIR_NP_SNAKE : 4;   // 15 warps: up to 128 registers per thread
+  static constexpr int kEpi = 12 - kProd;
   static constexpr int kMma = kProd + kEpi;
   static constexpr int kXLoad = kMma + 1;
   static constexpr int kWLoad = kMma + 2;
@@ -75,7 +89,7 @@ struct PairRoles {
 
 enum {  // mbarrier slots (w_full / w_empty rings follow)
   BX_FULL = 0, BX_EMPTY, BA1_FULL, BA1_EMPTY, BACC1_FULL, BACC1_EMPTY, BSCR_FULL, BSCR_EMPTY,
-  BA2_FULL, BA2_EMPTY, BACC2_FULL, BACC2_EMPTY, BNUM
+  BA2_FULL, BA2_EMPTY, BACC2_FULL, BACC2_EMPTY, BX2_FULL, BX2_EMPTY, BNUM
 };
 constexpr int kPairMaxRing = 64;
 
@@ -93,9 +107,10 @@ __device__ __forceinline__ void pair_mbar_arrive(uint64_t* bar) {
 }
 
 struct PairTile {
-  int b, t0, len;
+  int b, t0, len, tile;
 };
 __device__ __forceinline__ bool pair_tile(const PairArgs& a, int tile, PairTile& ti) {
+  ti.tile = tile;
   ti.b = tile / a.tiles_per_utt;
   ti.t0 = (tile - ti.b * a.tiles_per_utt) * a.T_out;
   ti.len = a.len ? min(__ldg(a.len + ti.b), a.L_max) : a.L_max;
@@ -106,13 +121,13 @@ __device__ __forceinline__ bool pair_tile(const PairArgs& a, int tile, PairTile&
 template <typename F1, typename F2>
 __device__ __forceinline__ void pair_schedule(const PairArgs& a, F1&& stage1, F2&& stage2) {
   // (one call site per stage: the stage bodies are inlined exactly once)
-  PairTile prev{0, 0, 0};
+  PairTile prev{0, 0, 0, 0};
   bool have_prev = false;
   uint32_t j = 0;
   int tile = blockIdx.x;
 #pragma unroll 1
   for (;;) {
-    PairTile cur{0, 0, 0};
+    PairTile cur{0, 0, 0, 0};
     bool have_cur = false;
 #pragma unroll 1
     while (tile < a.total_tiles && !have_cur) {
@@ -283,7 +298,7 @@ __device__ __noinline__ void pair_e2_tail(const char* xsrc, char* ydst, float4 f
   const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
 #pragma unroll 1
   for (int e = 0; e < n; ++e) {
-    const float xv = XF16 ? __half2float(reinterpret_cast<const __half*>(xsrc)[e]) : reinterpret_cast<const float*>(xsrc)[e];
+    const float xv = !xsrc ? 0.f : XF16 ? __half2float(reinterpret_cast<const __half*>(xsrc)[e]) : reinterpret_cast<const float*>(xsrc)[e];
     float val = fmaf(res_beta, xv, f[e]);
     if (accumulate) val += YF16 ? __half2float(reinterpret_cast<const __half*>(ydst)[e]) : reinterpret_cast<const float*>(ydst)[e];
     if constexpr (YF16) reinterpret_cast<__half*>(ydst)[e] = f16_sat(val);
@@ -291,7 +306,7 @@ __device__ __noinline__ void pair_e2_tail(const char* xsrc, char* ydst, float4 f
   }
 }
 
-template <bool XF16, bool YF16, bool ACC>
+template <bool XF16, bool YF16, bool ACC, bool RES = true>
 __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, int nsub, float* stg, const float* bias2_s,
                                         uint32_t tm, int q, int lane, int slab0, int slab_step, int slabs) {
   // items whose residual (and, for the multi-receptive-field sum, old y) vectors are in flight
@@ -303,11 +318,12 @@ __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, i
   const int limit = min(a.T_out, ti.len - ti.t0);   // valid output rows of this tile
   const int c0 = lane >> 2, g = lane & 3;           // this thread's slots of an item: channels c0, c0 + 8; rows 8g .. 8g+7 of the warp's 32
   const int r8 = q * 32 + 8 * g;
-  const char* xrow = reinterpret_cast<const char*>(a.x) + ((long long)ti.b * a.x_bs + ti.t0 + r8) * XE;
+  const char* xrow = reinterpret_cast<const char*>(a.res) + ((long long)ti.b * a.r_bs + ti.t0 + r8) * XE;
   char* yrow = reinterpret_cast<char*>(a.y) + ((long long)ti.b * a.y_bs + ti.t0 + r8) * YE;
   const float out_alpha = a.out_alpha, res_beta = a.res_beta;
   constexpr bool accumulate = ACC;
-  constexpr int PV = XV + (ACC ? YV : 0);           // residual vectors, then the old y vectors
+  constexpr int PV = (RES ? XV : 0) + (ACC ? YV : 0) + ((RES || ACC) ? 0 : 1);   // residual vectors, then the old y vectors
+  constexpr int YO = RES ? XV : 0;                  // first old-y vector
   uint4 pre[kD][2][PV];
   auto geom = [&](int k, int& sub, int& s) {
     sub = k / nsl;
@@ -319,14 +335,16 @@ __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, i
     const bool full = sub * kTileM + r8 + 8 <= limit;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const char* src = xrow + ((long long)(s * 16 + c0 + 8 * i) * a.x_ld + sub * kTileM) * XE;
+      if constexpr (RES) {
+        const char* src = xrow + ((long long)(s * 16 + c0 + 8 * i) * a.r_ld + sub * kTileM) * XE;
 #pragma unroll
-      for (int v = 0; v < XV; ++v) p[i][v] = full ? ldg128(src + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+        for (int v = 0; v < XV; ++v) p[i][v] = full ? ldg128(src + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+      }
       if constexpr (ACC) {
         const char* ysrc = yrow + ((long long)(s * 16 + c0 + 8 * i) * a.y_ld + sub * kTileM) * YE;
 #pragma unroll
         for (int v = 0; v < YV; ++v)
-          p[i][XV + v] = full ? *reinterpret_cast<const uint4*>(ysrc + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
+          p[i][YO + v] = full ? *reinterpret_cast<const uint4*>(ysrc + 16 * v) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
   };
@@ -361,19 +379,19 @@ __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, i
         f[0] = s0.x; f[1] = s0.y; f[2] = s0.z; f[3] = s0.w; f[4] = s1.x; f[5] = s1.y; f[6] = s1.z; f[7] = s1.w;
       }
       if (full) {
-        float r[8];
-        {
+        if constexpr (RES) {
+          float r[8];
           uint4 xv[XV];
 #pragma unroll
           for (int w = 0; w < XV; ++w) xv[w] = p[i][w];
           unpack8(xv, r);
-        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaf(res_beta, r[e], f[e]);
+          for (int e = 0; e < 8; ++e) f[e] = fmaf(res_beta, r[e], f[e]);
+        }
         if constexpr (ACC) {   // the multi-receptive-field sum: last pair of the 2nd / 3rd residual block only
           uint4 yv[YV];
 #pragma unroll
-          for (int w = 0; w < YV; ++w) yv[w] = p[i][XV + w];
+          for (int w = 0; w < YV; ++w) yv[w] = p[i][YO + w];
           float yo[8];
           unpack8(yv, yo);
 #pragma unroll
@@ -386,7 +404,7 @@ __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, i
           *reinterpret_cast<float4*>(ydst + 16) = make_float4(f[4], f[5], f[6], f[7]);
         }
       } else {
-        pair_e2_tail<XF16, YF16>(xrow + (crow * a.x_ld + sub * kTileM) * XE, ydst, make_float4(f[0], f[1], f[2], f[3]),
+        pair_e2_tail<XF16, YF16>(RES ? xrow + (crow * a.r_ld + sub * kTileM) * XE : nullptr, ydst, make_float4(f[0], f[1], f[2], f[3]),
                                  make_float4(f[4], f[5], f[6], f[7]), limit - o8, res_beta, accumulate);
       }
     }
@@ -412,7 +430,7 @@ __device__ __forceinline__ void pair_e2(const PairArgs& a, const PairTile& ti, i
 __device__ __noinline__ void pair_e2_generic(const PairArgs& a, const PairTile& ti, int nsub, const float* bias2_s, uint32_t tm,
                                              int q, int lane, int slab0, int slab_step, int slabs) {
   const int limit = min(a.T_out, ti.len - ti.t0);
-  const int XE = a.x_f16 ? 2 : 4, YE = a.y_f16 ? 2 : 4;
+  const int XE = a.r_f16 ? 2 : 4, YE = a.y_f16 ? 2 : 4;
 #pragma unroll 1
   for (int sub = 0; sub < nsub; ++sub) {
     const int o = sub * kTileM + q * 32 + lane;
@@ -425,16 +443,16 @@ __device__ __noinline__ void pair_e2_generic(const PairArgs& a, const PairTile& 
       tmem_ld_x16(tm + (uint32_t)(sub * a.C + s * 16), v);
       tmem_ld_wait();
       if (!ok) continue;
-      const char* xp = reinterpret_cast<const char*>(a.x) + ((long long)ti.b * a.x_bs + (long long)(s * 16) * a.x_ld + t) * XE;
+      const char* xp = a.res ? reinterpret_cast<const char*>(a.res) + ((long long)ti.b * a.r_bs + (long long)(s * 16) * a.r_ld + t) * XE : nullptr;
       char* yp = reinterpret_cast<char*>(a.y) + ((long long)ti.b * a.y_bs + (long long)(s * 16) * a.y_ld + t) * YE;
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
-        const float xv = a.x_f16 ? __half2float(*reinterpret_cast<const __half*>(xp)) : *reinterpret_cast<const float*>(xp);
+        const float xv = !xp ? 0.f : a.r_f16 ? __half2float(*reinterpret_cast<const __half*>(xp)) : *reinterpret_cast<const float*>(xp);
         float val = fmaf(a.res_beta, xv, fmaf(__uint_as_float(v[i]), a.out_alpha, bias2_s[s * 16 + i]));
         if (a.accumulate) val += a.y_f16 ? __half2float(*reinterpret_cast<const __half*>(yp)) : *reinterpret_cast<const float*>(yp);
         if (a.y_f16) *reinterpret_cast<__half*>(yp) = f16_sat(val);
         else *reinterpret_cast<float*>(yp) = val;
-        xp += (long long)a.x_ld * XE;
+        if (xp) xp += (long long)a.r_ld * XE;
         yp += (long long)a.y_ld * YE;
       }
     }
@@ -451,7 +469,7 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
   extern __shared__ __align__(128) uint8_t smem[];
   __half* A1 = reinterpret_cast<__half*>(smem + a.a1_off);
   __half* A2 = reinterpret_cast<__half*>(smem + a.a2_off);
-  uint8_t* X = smem + a.x_off;
+  uint8_t* Xbase = smem + a.x_off;
   __half* SCR = reinterpret_cast<__half*>(smem + a.scr_off);
   uint8_t* smW = smem + a.w_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
@@ -471,13 +489,15 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     if (lane == 0) {
       mbar_init(bars + BX_FULL, 1);
       mbar_init(bars + BX_EMPTY, NP);
+      mbar_init(bars + BX2_FULL, 1);       // single conv: the X tile is double buffered as well (tile j in buffer j & 1)
+      mbar_init(bars + BX2_EMPTY, NP);
       mbar_init(bars + BA1_FULL, NP);
       mbar_init(bars + BA1_EMPTY, 1);
       mbar_init(bars + BACC1_FULL, 1);
       mbar_init(bars + BACC1_EMPTY, NE);
       mbar_init(bars + BSCR_FULL, NE);
       mbar_init(bars + BSCR_EMPTY, NP);
-      mbar_init(bars + BA2_FULL, SNAKE ? NP : NE);
+      mbar_init(bars + BA2_FULL, (SNAKE || a.single) ? NP : NE);
       mbar_init(bars + BA2_EMPTY, 1);
       mbar_init(bars + BACC2_FULL, 1);
       mbar_init(bars + BACC2_EMPTY, NE);
@@ -500,10 +520,11 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
   }
   for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
     bias1_s[i] = a.bias1 ? __ldg(a.bias1 + i) : 0.f;
-    bias2_s[i] = a.bias2 ? __ldg(a.bias2 + i) * a.out_alpha : 0.f;
+    const float* bout = a.single ? a.bias1 : a.bias2;       // bias of the conv whose accumulators the output epilogue drains
+    bias2_s[i] = bout ? __ldg(bout + i) * a.out_alpha : 0.f;
     if constexpr (SNAKE) {
       snake1_s[i] = make_float2(__expf(__ldg(a.alpha1 + i)), 1.0f / (__expf(__ldg(a.beta1 + i)) + 1e-9f));
-      snake2_s[i] = make_float2(__expf(__ldg(a.alpha2 + i)), 1.0f / (__expf(__ldg(a.beta2 + i)) + 1e-9f));
+      if (!a.single) snake2_s[i] = make_float2(__expf(__ldg(a.alpha2 + i)), 1.0f / (__expf(__ldg(a.beta2 + i)) + 1e-9f));
     }
   }
   fence_proxy_async_smem();
@@ -526,26 +547,34 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     // ================================ producers ================================
     const int pw = warp;
     auto p1 = [&](const PairTile& ti, uint32_t j) {
-      pair_wait(bars + BX_FULL, j & 1);
-      pair_wait(bars + BA1_EMPTY, (j & 1) ^ 1);
+      // single conv: the two operand tiles (A1, A2 regions) are the two buffers of one conv, tile j uses buffer j & 1
+      const int buf = a.single ? (int)(j & 1) : 0;
+      const uint32_t use = a.single ? (j >> 1) : j;
+      const int xbuf = a.x_bufs == 2 ? buf : 0;
+      const uint32_t xuse = a.x_bufs == 2 ? use : j;
+      pair_wait(bars + (xbuf ? BX2_FULL : BX_FULL), xuse & 1);
+      pair_wait(bars + (buf ? BA2_EMPTY : BA1_EMPTY), (use & 1) ^ 1);
       if (threadIdx.x == 0) { ptrace(a, 12, j); ptrace(a, 0, j); }
       const int ta0 = ta0_of(ti), tx0 = tx0_of(ti);
+      __half* Adst = buf ? A2 : A1;
+      const uint8_t* X = Xbase + (size_t)xbuf * a.x_buf_bytes;
       if constexpr (SNAKE) {
-        if (a.x_f16) pair_snake_stage<true>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
-        else pair_snake_stage<false>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, A1, pw, NP, lane);
+        if (a.x_f16) pair_snake_stage<true>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, Adst, pw, NP, lane);
+        else pair_snake_stage<false>(X, a.PX, tx0, snake1_s, a.C, ta0, a.R1, a.Rp1, ti.len, Adst, pw, NP, lane);
       } else {
-        if (a.x_f16) pair_leaky_stage<true>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, A1, pw, NP, lane);
-        else pair_leaky_stage<false>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, A1, pw, NP, lane);
+        if (a.x_f16) pair_leaky_stage<true>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, Adst, pw, NP, lane);
+        else pair_leaky_stage<false>(X, a.PX, tx0, a.C, ta0, a.R1, a.Rp1, ti.len, a.slope, Adst, pw, NP, lane);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        pair_mbar_arrive(bars + BA1_FULL);
-        pair_mbar_arrive(bars + BX_EMPTY);
+        pair_mbar_arrive(bars + (buf ? BA2_FULL : BA1_FULL));
+        pair_mbar_arrive(bars + (xbuf ? BX2_EMPTY : BX_EMPTY));
       }
       if (threadIdx.x == 0) ptrace(a, 1, j);
     };
     auto p2 = [&](const PairTile& ti, uint32_t j) {
+      if (a.single) return;
       if constexpr (SNAKE) {
         pair_wait(bars + BSCR_FULL, j & 1);
         pair_wait(bars + BA2_EMPTY, (j & 1) ^ 1);
@@ -571,6 +600,7 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
     const int slabs = a.C >> 4;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     auto e1 = [&](const PairTile& ti, uint32_t j) {
+      if (a.single) return;                         // single conv: only the output epilogue below
       pair_wait_sleep(bars + BACC1_FULL, j & 1);
       if constexpr (SNAKE) pair_wait_sleep(bars + BSCR_EMPTY, (j & 1) ^ 1);
       else pair_wait_sleep(bars + BA2_EMPTY, (j & 1) ^ 1);
@@ -628,23 +658,28 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       }
       if (ew == 0 && lane == 0) ptrace(a, 5, j);
     };
+    // output epilogue: conv2 of a pair, or the conv of the single mode (tile j in accumulator buffer j & 1).  One call
+    // site, so that its variants are inlined once.
     auto e2 = [&](const PairTile& ti, uint32_t j) {
-      pair_wait_sleep(bars + BACC2_FULL, j & 1);
+      const int buf = a.single ? (int)(j & 1) : 1;
+      const uint32_t use = a.single ? (j >> 1) : j;
+      pair_wait_sleep(bars + (buf ? BACC2_FULL : BACC1_FULL), use & 1);
       tc_fence_after();
       if (ew == 0 && lane == 0) ptrace(a, 6, j);
-      const uint32_t tm = acc2_col + lane_base;
+      const uint32_t tm = (buf ? acc2_col : acc1_col) + lane_base;
+      const int nsub = a.single ? nsub1_of(ti) : nsub2_of(ti);
       float* stg = stage_s + ew * kStageFloats;
-      const int nsub2 = nsub2_of(ti);
       if (a.dbg_skip & 2) {
-      } else if (a.x_f16 && a.y_f16) {   // the generators' fp16 streams: the two hot variants, inlined
-        if (a.accumulate) pair_e2<true, true, true>(a, ti, nsub2, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
-        else pair_e2<true, true, false>(a, ti, nsub2, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+      } else if (a.y_f16 && (a.r_f16 || !a.res)) {   // the generators' fp16 streams: the hot variants, inlined
+        if (!a.res) pair_e2<true, true, false, false>(a, ti, nsub, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+        else if (a.accumulate) pair_e2<true, true, true>(a, ti, nsub, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+        else pair_e2<true, true, false>(a, ti, nsub, stg, bias2_s, tm, q, lane, slab0, slab_step, slabs);
       } else {
-        pair_e2_generic(a, ti, nsub2, bias2_s, tm, q, lane, slab0, slab_step, slabs);
+        pair_e2_generic(a, ti, nsub, bias2_s, tm, q, lane, slab0, slab_step, slabs);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) pair_mbar_arrive(bars + BACC2_EMPTY);
+      if (lane == 0) pair_mbar_arrive(bars + (buf ? BACC2_EMPTY : BACC1_EMPTY));
       if (ew == 0 && lane == 0) ptrace(a, 7, j);
     };
     pair_schedule(a, e1, e2);
@@ -702,20 +737,23 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       first = false;
     };
     auto m1 = [&](const PairTile& ti, uint32_t j) {
-      pair_wait_sleep(bars + BA1_FULL, j & 1);
-      pair_wait_sleep(bars + BACC1_EMPTY, (j & 1) ^ 1);
+      const int buf = a.single ? (int)(j & 1) : 0;
+      const uint32_t use = a.single ? (j >> 1) : j;
+      pair_wait_sleep(bars + (buf ? BA2_FULL : BA1_FULL), use & 1);
+      pair_wait_sleep(bars + (buf ? BACC2_EMPTY : BACC1_EMPTY), (use & 1) ^ 1);
       __syncwarp();
       if (lane == 0) ptrace(a, 8, j);
       tc_fence_after();
-      conv(smem_u32(A1), a.Rp1, a.dil, nsub1_of(ti), acc1_col, 0, first1);
+      conv(smem_u32(buf ? A2 : A1), a.Rp1, a.dil, nsub1_of(ti), buf ? acc2_col : acc1_col, 0, first1);
       if (elect_one()) {
-        umma_commit(bars + BA1_EMPTY);
-        umma_commit(bars + BACC1_FULL);
+        umma_commit(bars + (buf ? BA2_EMPTY : BA1_EMPTY));
+        umma_commit(bars + (buf ? BACC2_FULL : BACC1_FULL));
       }
       __syncwarp();
       if (lane == 0) ptrace(a, 9, j);
     };
     auto m2 = [&](const PairTile& ti, uint32_t j) {
+      if (a.single) return;
       pair_wait_sleep(bars + BA2_FULL, j & 1);
       pair_wait_sleep(bars + BACC2_EMPTY, (j & 1) ^ 1);
       __syncwarp();
@@ -733,23 +771,48 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
   } else if (warp == Rl::kXLoad) {
     // ================================ X loader ================================
     // one bulk copy per channel row: global [b][c][lo, hi) -> X[c][lo - tx0 ...]; lanes share the rows
-    auto xl = [&](const PairTile& ti, uint32_t j) {
-      pair_wait_sleep(bars + BX_EMPTY, (j & 1) ^ 1);
-      __syncwarp();
-      const int tx0 = tx0_of(ti);
+    // rows [lo, hi) of the X tile of `ti` (16-byte multiples, inside the utterance's padded row)
+    auto x_range = [&](const PairTile& ti, int& lo, int& hi) {
       const int ta0 = ta0_of(ti);
       const int tx_end = (ta0 + a.R1 + (SNAKE ? 6 : 0) + 7) & ~7;
       const int unit = 16 / esz;
       const int len_al = min((ti.len + unit - 1) / unit * unit, a.x_ld);
-      const int lo = max(tx0, 0), hi = min(tx_end, len_al);
+      lo = max(tx0_of(ti), 0);
+      hi = min(tx_end, len_al);
+    };
+    auto xl = [&](const PairTile& ti, uint32_t j) {
+      // The X tile is single: the load of tile j can only start when the producers are done with tile j-1 and is then on
+      // their critical path.  Pull this CTA's NEXT tile into L2 while the current one is being staged, so that the
+      // exposed part is an L2 hit (measured 6.2 K cycles per tile from DRAM).
+      {
+        PairTile nx;
+        const int ntile = ti.tile + (int)gridDim.x;
+        if (ntile < a.total_tiles && pair_tile(a, ntile, nx)) {
+          int nlo, nhi;
+          x_range(nx, nlo, nhi);
+          const uint32_t nb = (uint32_t)(nhi - nlo) * (uint32_t)esz;
+          const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(a.x) + ((long long)nx.b * a.x_bs + nlo) * esz;
+#pragma unroll 1
+          for (int c = lane; c < a.C; c += 32)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc + (long long)c * a.x_ld * esz), "r"(nb) : "memory");
+        }
+      }
+      const int buf = a.x_bufs == 2 ? (int)(j & 1) : 0;
+      const uint32_t use = a.x_bufs == 2 ? (j >> 1) : j;
+      uint64_t* xfull = bars + (buf ? BX2_FULL : BX_FULL);
+      pair_wait_sleep(bars + (buf ? BX2_EMPTY : BX_EMPTY), (use & 1) ^ 1);
+      __syncwarp();
+      const int tx0 = tx0_of(ti);
+      int lo, hi;
+      x_range(ti, lo, hi);
       const uint32_t nbytes = (uint32_t)(hi - lo) * (uint32_t)esz;
-      if (lane == 0) mbar_arrive_expect_tx(bars + BX_FULL, nbytes * (uint32_t)a.C);
+      if (lane == 0) mbar_arrive_expect_tx(xfull, nbytes * (uint32_t)a.C);
       __syncwarp();
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a.x) + ((long long)ti.b * a.x_bs + lo) * esz;
-      uint8_t* dst = X + (long long)(lo - tx0) * esz;
+      uint8_t* dst = Xbase + (size_t)buf * a.x_buf_bytes + (long long)(lo - tx0) * esz;
 #pragma unroll 1
       for (int c = lane; c < a.C; c += 32)
-        bulk_copy_g2s(dst + (long long)c * a.PX * esz, src + (long long)c * a.x_ld * esz, nbytes, bars + BX_FULL);
+        bulk_copy_g2s(dst + (long long)c * a.PX * esz, src + (long long)c * a.x_ld * esz, nbytes, xfull);
     };
     auto none = [&](const PairTile&, uint32_t) {};
     pair_schedule(a, xl, none);
@@ -767,7 +830,7 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
       }
       if (any) {
 #pragma unroll 1
-        for (int c = 0; c < 2 * a.n_chunks; ++c) {
+        for (int c = 0; c < (a.single ? 1 : 2) * a.n_chunks; ++c) {
           if (elect_one()) {
             const uint8_t* src = c < a.n_chunks ? w1 + (long long)c * a.chunk_bytes : w2 + (long long)(c - a.n_chunks) * a.chunk_bytes;
             mbar_arrive_expect_tx(w_full + c, a.chunk_bytes);
@@ -792,7 +855,9 @@ __global__ void __launch_bounds__(PairRoles<SNAKE>::kThreads, 1) respair_kernel(
         }
       };
       auto s1 = [&](const PairTile&, uint32_t) { stream(w1); };
-      auto s2 = [&](const PairTile&, uint32_t) { stream(w2); };
+      auto s2 = [&](const PairTile&, uint32_t) {
+        if (!a.single) stream(w2);
+      };
       pair_schedule(a, s1, s2);
     }
   }
@@ -843,13 +908,15 @@ static int plane_rows(int rows) { return rows % 4 == 0 ? rows + 1 : rows; }   //
 
 // Largest tile (S sub-tiles of 128 rows) whose buffers fit; weights resident if both convs fit next to them.
 static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
+  const bool single = a.single != 0;
+  const int nconv = single ? 1 : 2;
   const ConvGeom g = conv_geom(a.C, a.C, a.K, 0, TB200_PREC_F16);
   if (g.n_ntiles != 1 || g.NT != a.C) return fail(TB200_E_BADARG, "respair: C=%d must be a multiple of 16, <= 256", a.C);
   a.KC = g.KC; a.n_kchunks = g.n_kchunks; a.n_chunks = g.ntaps * g.n_kchunks;
   a.chunk_bytes = (int)(g.chunk_elems * 2);
-  a.h = snake ? 6 : 0;
-  a.p2 = (a.K - 1) / 2;
-  a.p1 = a.p2 * a.dil;
+  a.p1 = (a.K - 1) / 2 * a.dil;
+  a.h = (snake && !single) ? 6 : 0;      // rows of u1 the second activation needs on either side (pair only)
+  a.p2 = single ? 0 : (a.K - 1) / 2;
   const int esz = a.x_f16 ? 2 : 4;
   // NR = rows of conv1 per tile: a multiple of 32 (an epilogue warp owns 32 accumulator rows), the last 128-row
   // sub-tile at least half used; the largest that fits wins (halo recompute and the per-segment warm-up of the
@@ -869,28 +936,34 @@ static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
     // operand planes: the rows a conv reads past the last written one belong to discarded output rows only; they
     // alias the next plane / the buffer behind the tile (any finite or non-finite value is harmless there)
     const int R1 = NR + 2 * a.p1, Rp1 = plane_rows(R1);
-    const int R2v = NR - 2 * a.h, Rp2 = plane_rows(R2v);
+    const int R2v = NR - 2 * a.h, Rp2 = single ? Rp1 : plane_rows(R2v);   // single conv: the A2 region is A1's second buffer
     const int a1_bytes = (a.C / 8) * Rp1 * 16, a2_bytes = (a.C / 8) * Rp2 * 16;
-    const int PX = round_pitch(R1 + 32, esz), x_bytes = a.C * PX * esz + 128;   // + look-ahead reads of the last row
-    const int PS = snake ? round_pitch(NR + 16, 2) : 0, scr_bytes = snake ? a.C * PS * 2 + 128 : 0;
+    const int PX = round_pitch(R1 + 32, esz), x_buf = a.C * PX * esz + 128;     // + look-ahead reads of the last row
+    // One X buffer: its load is then exposed between two tiles of the single mode (~5 K cycles of ~25 K, the next tile is
+    // prefetched into L2), but two buffers cost a third of the tile height and measured slower (C = 64, K = 3 snake:
+    // 2.71 vs 2.51 ms per pair of launches): with every role busy all the time the SM's issue rate is the limit.
+    const int x_bufs = 1;
+    const int x_bytes = x_bufs * x_buf;
+    const int PS = (snake && !single) ? round_pitch(NR + 16, 2) : 0, scr_bytes = PS ? a.C * PS * 2 + 128 : 0;
     const int stage_bytes = (snake ? PairRoles<true>::kEpi : PairRoles<false>::kEpi) * kStageFloats * 4;
     const int fixed = (BNUM + 2 * kPairMaxRing) * 8 + 6 * a.C * 4 + 16 + 256 + stage_bytes;
     const long long avail = (long long)smem_cap - a1_bytes - a2_bytes - x_bytes - scr_bytes - fixed;
-    const long long w_total = 2LL * a.n_chunks * a.chunk_bytes;
+    const long long w_total = (long long)nconv * a.n_chunks * a.chunk_bytes;
     int resident = 0, ring = 0;
-    if (w_total <= avail && 2 * a.n_chunks <= kPairMaxRing) {
+    if (w_total <= avail && nconv * a.n_chunks <= kPairMaxRing) {
       resident = 1;
-      ring = 2 * a.n_chunks;
+      ring = nconv * a.n_chunks;
     } else {
       // streamed weights: a chunk is consumed in a few hundred cycles and refilled from L2 in one to two thousand, so
       // the ring must hold a few chunks and >= 24 KB (a 2-slot ring of 2 KB chunks made the K = 11, C = 32 pairs 2x
       // slower than a smaller tile with resident weights; 3 x 8 KB at C = 64 measured as good as resident weights)
       long long slots = avail / a.chunk_bytes;
       if (slots > 16) slots = 16;
-      if (slots > 2 * a.n_chunks) slots = 2 * a.n_chunks;
+      if (slots > nconv * a.n_chunks) slots = nconv * a.n_chunks;
       if (slots < 3 || slots * a.chunk_bytes < 24 * 1024) continue;
       ring = (int)slots;
     }
+    a.x_buf_bytes = x_buf; a.x_bufs = x_bufs;
     a.S = S; a.NR = NR; a.T_out = T_out; a.R1 = R1; a.Rp1 = Rp1; a.R2v = R2v; a.Rp2 = Rp2; a.PX = PX; a.PS = PS;
     a.resident = resident; a.ring_slots = ring;
     a.tiles_per_utt = (a.L_max + T_out - 1) / T_out;
@@ -972,6 +1045,7 @@ extern "C" int tb200_respair(const tb200_respair_params* p, void* stream_v) {
   a.B = p->B; a.C = p->C; a.L_max = p->L_max; a.K = p->K; a.dil = p->dilation;
   a.x_f16 = p->x_dtype == TB200_F16; a.y_f16 = p->y_dtype == TB200_F16;
   a.slope = p->act_slope; a.out_alpha = p->out_alpha; a.res_beta = p->res_beta; a.accumulate = p->accumulate;
+  a.res = p->x; a.r_bs = p->x_bs; a.r_ld = p->x_ld; a.r_f16 = a.x_f16; a.single = 0;
   rc = plan_pair(a, snake, d->max_smem, d->sm_count);
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -984,6 +1058,61 @@ extern "C" int tb200_respair(const tb200_respair_params* p, void* stream_v) {
   }
   if (g_pair_debug)
     fprintf(stderr, "tb200 respair plan: C=%d K=%d dil=%d snake=%d L=%d x_f16=%d -> S=%d T_out=%d R1=%d tiles=%d %s ring=%d smem=%d tmem=%d\n",
+            a.C, a.K, a.dil, (int)snake, a.L_max, a.x_f16, a.S, a.T_out, a.R1, a.total_tiles, a.resident ? "resident" : "streamed",
+            a.ring_slots, a.smem_total, a.tmem_cols);
+  return snake ? launch_pair<true>(a, d, stream) : launch_pair<false>(a, d, stream);
+}
+
+// One convolution through the same pipeline (TMA-fed X tile, smem-fed staging, double-buffered operand tiles and
+// accumulators, vectorised epilogue): same parameter block as tb200_conv1d.
+extern "C" int tb200_conv1d_staged(const tb200_conv1d_params* p, void* stream_v) {
+  if (!p || !p->x || !p->y || !p->w_packed) return fail(TB200_E_BADARG, "conv1d_staged: null pointer");
+  if (p->B <= 0 || p->C_in <= 0 || p->L_in_max <= 0) return fail(TB200_E_BADARG, "conv1d_staged: empty shape");
+  const bool snake = p->act == TB200_ACT_AA_SNAKEBETA;
+  if (p->precision != TB200_PREC_F16 || p->transposed_stride != 0 || p->out_act != TB200_OUT_NONE || p->C_in != p->C_out ||
+      p->C_in % 32 || p->C_in > 128 || !(p->K & 1) || p->K > kMaxTaps || p->dilation < 1 || p->pad != (p->K - 1) / 2 * p->dilation ||
+      (!snake && p->act != TB200_ACT_LEAKY_RELU))
+    return fail(TB200_E_BADARG, "conv1d_staged: needs fp16 operands, C_in == C_out in {32,64,96,128}, an odd 'same'-padded kernel, "
+                                "LeakyReLU or anti-aliased SnakeBeta in front and no output activation");
+  if (snake && (!p->act_alpha || !p->act_beta)) return fail(TB200_E_BADARG, "conv1d_staged: snake activation needs alpha/beta");
+  if (!snake && (p->act_slope < 0.f || p->act_slope > 1.f)) return fail(TB200_E_BADARG, "conv1d_staged: LeakyReLU slope must be in [0, 1]");
+  if (PairRoles<true>::kProd % (p->C_in / 32)) return fail(TB200_E_BADARG, "conv1d_staged: C=%d does not divide the producer warps", p->C_in);
+  const int ux = p->x_dtype == TB200_F16 ? 8 : 4, uy = p->y_dtype == TB200_F16 ? 8 : 4, ur = p->r_dtype == TB200_F16 ? 8 : 4;
+  auto aligned = [&](const void* ptr, int64_t bs, int32_t ld, int unit) {
+    return !(reinterpret_cast<uintptr_t>(ptr) & 15) && ld % unit == 0 && bs % unit == 0 && ld >= (p->L_in_max + unit - 1) / unit * unit;
+  };
+  if (!aligned(p->x, p->x_bs, p->x_ld, ux) || !aligned(p->y, p->y_bs, p->y_ld, uy) || (p->residual && !aligned(p->residual, p->r_bs, p->r_ld, ur)))
+    return fail(TB200_E_BADARG, "conv1d_staged: x, y and residual must be 16-byte aligned with 16-byte multiples as row pitch and batch stride");
+  if (p->x == p->y) return fail(TB200_E_BADARG, "conv1d_staged: in-place operation is not supported (tiles read their neighbours' halos)");
+  const long long lim = 1LL << 31;
+  if ((long long)p->B * p->x_bs >= lim || (long long)p->B * p->y_bs >= lim || (p->residual && (long long)p->B * p->r_bs >= lim))
+    return fail(TB200_E_BADARG, "conv1d_staged: tensors must be addressable with 32-bit element offsets");
+  PairDevice* d = nullptr;
+  int rc = pair_device(d);
+  if (rc) return rc;
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.single = 1;
+  a.x = p->x; a.y = p->y; a.len = p->len_in;
+  a.bias1 = p->bias; a.alpha1 = p->act_alpha; a.beta1 = p->act_beta;
+  a.w1 = p->w_packed; a.w2 = p->w_packed;
+  a.x_bs = p->x_bs; a.y_bs = p->y_bs; a.x_ld = p->x_ld; a.y_ld = p->y_ld;
+  a.B = p->B; a.C = p->C_in; a.L_max = p->L_in_max; a.K = p->K; a.dil = p->dilation;
+  a.x_f16 = p->x_dtype == TB200_F16; a.y_f16 = p->y_dtype == TB200_F16;
+  a.slope = p->act_slope; a.out_alpha = p->out_alpha; a.res_beta = p->residual ? p->res_beta : 0.f; a.accumulate = p->accumulate;
+  a.res = p->residual; a.r_bs = p->r_bs; a.r_ld = p->r_ld; a.r_f16 = p->r_dtype == TB200_F16;
+  rc = plan_pair(a, snake, d->max_smem, d->sm_count);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  a.dbg_skip = g_pair_skip;
+  a.trace = nullptr;
+  if (g_pair_trace_on) {
+    if (!g_pair_trace) TB200_CUDA_CHECK(cudaMalloc(&g_pair_trace, kPairTraceLen * sizeof(long long)));
+    TB200_CUDA_CHECK(cudaMemsetAsync(g_pair_trace, 0, kPairTraceLen * sizeof(long long), stream));
+    a.trace = g_pair_trace;
+  }
+  if (g_pair_debug)
+    fprintf(stderr, "tb200 staged conv plan: C=%d K=%d dil=%d snake=%d L=%d x_f16=%d -> S=%d T_out=%d R1=%d tiles=%d %s ring=%d smem=%d tmem=%d\n",
             a.C, a.K, a.dil, (int)snake, a.L_max, a.x_f16, a.S, a.T_out, a.R1, a.total_tiles, a.resident ? "resident" : "streamed",
             a.ring_slots, a.smem_total, a.tmem_cols);
   return snake ? launch_pair<true>(a, d, stream) : launch_pair<false>(a, d, stream);

@@ -88,9 +88,20 @@ class ConvLayer:
         return length * self.up if self.up else length
 
     @_on_device
+    def staged_ok(self, x, out, residual, act, out_act):
+        """Can this call run through tb200_conv1d_staged (TMA-fed tiles; see include/toucan_b200.h)?"""
+        def al(t):
+            unit = 16 // t.element_size()
+            return t.data_ptr() % 16 == 0 and t.stride(1) % unit == 0 and t.stride(0) % unit == 0
+        return (self.precision == PREC_F16 and self.up == 0 and self.c_in == self.c_out and self.c_in in (32, 64, 128)
+                and self.k % 2 == 1 and self.pad == (self.k - 1) // 2 * self.dilation and out_act == OUT_NONE
+                and act in (ACT_LEAKY_RELU, ACT_AA_SNAKEBETA) and al(x) and al(out) and (residual is None or al(residual))
+                and x.data_ptr() != out.data_ptr())
+
     def __call__(self, x, lengths, out, l_in_max=None, act=ACT_NONE, slope=0.0, alpha=None, beta=None, out_act=OUT_NONE,
-                 out_alpha=1.0, residual=None, res_beta=1.0, accumulate=False):
-        """x (B,C_in,L) -> out (B,C_out,L_out), both NCL with contiguous rows.  lengths: int32 (B) or None."""
+                 out_alpha=1.0, residual=None, res_beta=1.0, accumulate=False, staged=False):
+        """x (B,C_in,L) -> out (B,C_out,L_out), both NCL with contiguous rows.  lengths: int32 (B) or None.
+        staged=True: use tb200_conv1d_staged when the call qualifies (same result, TMA-fed pipeline)."""
         global LAUNCHES
         _require_cuda(x, out, residual, lengths)
         if x.stride(2) != 1 or out.stride(2) != 1 or x.shape[1] != self.c_in or out.shape[1] != self.c_out:
@@ -116,7 +127,10 @@ class ConvLayer:
         p.y, p.y_dtype, p.y_bs, p.y_ld = out.data_ptr(), _dtype_code(out), out.stride(0), out.stride(1)
         if self.out_len(p.L_in_max) > out.shape[2]:
             raise _lib.EngineError("conv1d: output buffer too short")
-        _lib.check(_lib.load().tb200_conv1d(ctypes.byref(p), _lib.stream_ptr()), "tb200_conv1d")
+        if staged and self.staged_ok(x, out, residual, act, out_act) and p.L_in_max <= min(x.stride(1), out.stride(1)):
+            _lib.check(_lib.load().tb200_conv1d_staged(ctypes.byref(p), _lib.stream_ptr()), "tb200_conv1d_staged")
+        else:
+            _lib.check(_lib.load().tb200_conv1d(ctypes.byref(p), _lib.stream_ptr()), "tb200_conv1d")
         LAUNCHES += 1
         return out
 

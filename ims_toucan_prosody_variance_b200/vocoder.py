@@ -106,7 +106,7 @@ class _GeneratorBase(torch.nn.Module):
             return False
         snake = self._names()["act"] is not None
         if snake:
-            return kernel <= 7 and channels != 64
+            return (kernel <= 7 and channels != 64) or (kernel == 3 and channels == 64)
         return kernel <= 7 or channels == 64
 
     # -- workspace ---------------------------------------------------------------------------

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TB200_VERSION 103
+#define TB200_VERSION 104
 
 enum {
   TB200_OK = 0,
@@ -156,6 +156,16 @@ typedef struct tb200_respair_params {
 } tb200_respair_params;
 
 int tb200_respair(const tb200_respair_params* p, void* stream);
+
+/* tb200_conv1d_staged -- ONE 'same'-padded C -> C convolution of the generators' residual stacks through the
+ * pipeline of tb200_respair: the raw input tile is brought into shared memory by the TMA engine (cp.async.bulk), the
+ * prologue activation (LeakyReLU / anti-aliased SnakeBeta) is staged from shared memory into double-buffered
+ * tensor-core operand tiles, the epilogue (bias, out_alpha, res_beta * residual, accumulate) moves 16 bytes per
+ * access.  Same parameter block and result as tb200_conv1d for the cases it accepts: precision TB200_PREC_F16,
+ * C_in == C_out in {32, 64, 128}, odd K with pad == (K-1)/2*dilation, transposed_stride 0, act LEAKY_RELU or
+ * AA_SNAKEBETA, out_act NONE; x, y, residual 16-byte aligned rows (pitch / batch stride multiples of 16 bytes);
+ * y must not alias x.  Returns TB200_E_BADARG otherwise (callers fall back to tb200_conv1d).               */
+int tb200_conv1d_staged(const tb200_conv1d_params* p, void* stream);
 
 /* Debugging aid: like tb200_debug_trace_read, for tb200_respair (16 stamps per tile).            */
 int tb200_respair_trace_read(int64_t* host_out, int32_t n);

@@ -13,7 +13,7 @@ TOL = {"fp32": 2e-5, "tf32": 2e-3, "f16": 2e-3}
 
 def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0, snake=False, residual=False,
          out_act=0, out_alpha=1.0, res_beta=1.0, accumulate=False, x_half=False, y_half=False, seed=0,
-         y_misalign=False, alpha_scale=0.3):
+         y_misalign=False, alpha_scale=0.3, staged=False):
     from ims_toucan_prosody_variance_b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, Cin, L, generator=g)
@@ -61,14 +61,27 @@ def _run(cuda, prec, B, Cin, Cout, K, dil, L, lens=None, up=0, act=0, slope=0.0,
     yd = y0.to(cuda)
     if y_half:
         yd = yd.half()
+    if staged:   # 16-byte aligned rows, as the generators' workspaces have
+        def pad8(t):
+            full = torch.zeros(t.shape[0], t.shape[1], (t.shape[2] + 7) // 8 * 8, dtype=t.dtype, device=cuda)
+            full[:, :, :t.shape[2]] = t
+            return full[:, :, :t.shape[2]]
+        xd, yd = pad8(xd), pad8(yd)
     if y_misalign:   # a view whose rows start one element off: no 8-byte (fp32) / 4-byte (fp16) alignment for paired stores
         full = torch.zeros(B, Cout, Lout + 2 + (Lout & 1), dtype=yd.dtype, device=cuda)
         full[:, :, 1:1 + Lout] = yd
         yd = full[:, :, 1:1 + Lout]
     lt = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    resd = res.to(cuda) if residual else None
+    if staged and residual:
+        resd = pad8(resd.half() if y_half else resd)
+        if y_half:
+            ref = ref + 0   # (the fp16 rounding of the residual is inside the tolerance of fp16 outputs)
+    if staged:
+        assert layer.staged_ok(xd, yd, resd, 2 if snake else act, out_act), "the staged kernel must accept this case"
     layer(xd, lt, yd, act=2 if snake else act, slope=slope, alpha=alpha.to(cuda) if snake else None,
           beta=beta.to(cuda) if snake else None, out_act=out_act, out_alpha=out_alpha,
-          residual=res.to(cuda) if residual else None, res_beta=res_beta, accumulate=accumulate)
+          residual=resd, res_beta=res_beta, accumulate=accumulate, staged=staged)
     torch.cuda.synchronize()
     got = yd.float().cpu()
     tol = max(TOL[prec], 1e-3) if y_half else TOL[prec]  # fp16 output rounding: 2^-11 relative
@@ -210,3 +223,26 @@ def test_ragged_ctas_without_valid_tiles_then_relaunch(cuda):
     lens = [2000] + [3] * 200 + [2000]
     for seed in range(3):
         _run(cuda, "f16", B=len(lens), Cin=32, Cout=32, K=3, dil=1, L=2000, lens=lens, act=1, slope=0.1, residual=True, seed=seed)
+
+
+@pytest.mark.parametrize("snake", [False, True])
+@pytest.mark.parametrize("C,K,dil", [(32, 3, 1), (64, 7, 3), (64, 11, 5), (128, 11, 5), (128, 3, 1)])
+def test_staged_single_conv(cuda, snake, C, K, dil):
+    """tb200_conv1d_staged (one conv through the TMA-fed pipeline) == tb200_conv1d's contract: ragged, with and without
+    residual / accumulate, fp32 and fp16 streams."""
+    kw = dict(B=3, Cin=C, Cout=C, K=K, dil=dil, L=900, lens=[900, 257, 6], snake=snake, act=0 if snake else 1, slope=0.1,
+              staged=True)
+    _run(cuda, "f16", seed=C + K, x_half=True, y_half=True, **kw)                                  # conv1 of a pair
+    _run(cuda, "f16", seed=C + K + 1, x_half=True, y_half=True, residual=True, **kw)               # conv2 of a pair
+    _run(cuda, "f16", seed=C + K + 2, x_half=True, y_half=True, residual=True, out_alpha=1 / 3, res_beta=1 / 3,
+         accumulate=True, **kw)                                                                    # ... folded into the MRF mean
+    if C <= 64:
+        _run(cuda, "f16", seed=C + K + 3, residual=True, **kw)                                     # fp32 streams
+
+
+def test_staged_many_tiles_and_empty_utterances(cuda):
+    lens = [5000, 0, 1, 127, 128, 129, 2047, 4999, 12, 0, 950, 234, 235, 468]
+    for snake in (False, True):
+        for _ in range(2):
+            _run(cuda, "f16", B=len(lens), Cin=32, Cout=32, K=3, dil=1, L=5000, lens=lens, snake=snake, act=0 if snake else 1,
+                 slope=0.1, residual=True, x_half=True, y_half=True, staged=True, seed=7)

@@ -14,7 +14,9 @@ from ims_toucan_prosody_variance_b200 import ops  # noqa: E402
 C, K, dil, L, B, snake = (int(v) for v in sys.argv[1:7])
 dt = torch.float16 if (len(sys.argv) > 7 and sys.argv[7] == "f16") else torch.float32
 reps = int(sys.argv[8]) if len(sys.argv) > 8 else 5
-unfused = len(sys.argv) > 9 and sys.argv[9] == "unfused"
+mode = sys.argv[9] if len(sys.argv) > 9 else "fused"     # fused | unfused (two tb200_conv1d) | staged (two tb200_conv1d_staged)
+unfused = mode in ("unfused", "staged")
+staged = mode == "staged"
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 w1 = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
@@ -26,15 +28,16 @@ pair = ops.ResPair(c1, c2, act if snake else None, act if snake else None)
 Lp = (L + 7) // 8 * 8
 x = torch.randn(B, C, Lp, device=dev).to(dt)
 y = torch.zeros(B, C, Lp, device=dev, dtype=dt)
-t = torch.zeros(B, C, Lp + 8, device=dev, dtype=torch.float16)
+t = torch.zeros(B, C, Lp, device=dev, dtype=torch.float16)
 lens = torch.full((B,), L, dtype=torch.int32, device=dev)
 
 
 def step():
     if unfused:
         a = 2 if snake else 1
-        c1(x, lens, t, l_in_max=L, act=a, slope=0.1, alpha=act[0], beta=act[1])
-        c2(t, lens, y, l_in_max=L, act=a, slope=0.1, alpha=act[0], beta=act[1], residual=x)
+        c1(x, lens, t, l_in_max=L, act=a, slope=0.1, alpha=act[0], beta=act[1], staged=staged)
+        c2(t, lens, y, l_in_max=L, act=a, slope=0.1, alpha=act[0], beta=act[1], residual=None if os.environ.get("PM_NORES") else x,
+           staged=staged)
     else:
         pair(x, lens, y, l_max=L, slope=0.1)
 
@@ -52,11 +55,11 @@ ms = e0.elapsed_time(e1) / reps
 flops = 2.0 * B * L * C * C * K * 2
 esz = 2 if dt == torch.float16 else 4
 byts = B * L * C * esz * 2
-print(f"C={C} K={K} dil={dil} L={L} B={B} snake={snake} {sys.argv[7] if len(sys.argv) > 7 else 'f32'} {'unfused' if unfused else 'fused'}: "
+print(f"C={C} K={K} dil={dil} L={L} B={B} snake={snake} {sys.argv[7] if len(sys.argv) > 7 else 'f32'} {mode}: "
       f"{ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s (algorithmic: x in + y out)  "
       f"{ms * 1e-3 * 1.9e9 * 148 / (B * L * C):.3f} SM-cycles/element @1.9GHz")
 
-if os.environ.get("TB200_TRACE") and not unfused:
+if os.environ.get("TB200_TRACE") and mode != "unfused":
     import ctypes
 
     from ims_toucan_prosody_variance_b200 import _lib
