@@ -321,7 +321,7 @@ def run_tts_workload(args, rank, local_rank, world, dev, dist):
 def run_config4(args, rank, world, dev, dist):
     """BASELINE.json configs[3]: ONE global batch of 512 ragged utterances (20..200 phonemes), partitioned by utterance
     over the ranks with sharding.partition_lpt (longest-processing-time first on the estimated cost), each rank running
-    text -> wave through TextToWave (length buckets of <= 64 utterances) with no collective on the data path; the ranks
+    text -> wave through TextToWave (length-sorted batches of <= 128 utterances) with no collective on the data path; the ranks
     then exchange output lengths and timings.  Strong scaling: the total work is fixed as N grows.  Returns the extra
     `config4` object of the bench line (on every rank; rank 0 prints it)."""
     import random
@@ -337,7 +337,12 @@ def run_config4(args, rank, world, dev, dist):
     tts = tb.ToucanTTS(weights=factory.make_state_dict("toucantts", 1234), precision=args.acoustic_precision).to(dev)
     tts.store_inverse_all()
     voc, _ = build_generator(args.vocoder, args.precision, dev, args.activations)
-    eng = tb.TextToWave(tts, voc)
+    kw = {}
+    if args.config4_max_batch:
+        kw["max_batch"] = args.config4_max_batch
+    if args.config4_padding_ratio:
+        kw["max_padding_ratio"] = args.config4_padding_ratio
+    eng = tb.TextToWave(tts, voc, **kw)
     texts = [factory.make_phoneme_tensor(lens[i], 5000 + i) for i in mine]
     emb = torch.stack([factory.make_utterance_embedding(i) for i in mine]) if mine else torch.zeros((0, 64))
     lang = torch.full((len(mine),), 12, dtype=torch.int64)
@@ -398,6 +403,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra sharded 512-utterance text->wave run")
     ap.add_argument("--config4-utterances", type=int, default=512)
+    ap.add_argument("--config4-max-batch", type=int, default=None, help="TextToWave bucket size (default: the engine's)")
+    ap.add_argument("--config4-padding-ratio", type=float, default=None, help="TextToWave longest/shortest ratio per bucket")
+    ap.add_argument("--config4-only", action="store_true", help="debug: print only the config4 object")
     args = ap.parse_args()
     args.batch_given = args.batch is not None
     if args.batch is None:
@@ -421,6 +429,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config4_only:
+        c4 = run_config4(args, rank, world, dev, dist)
+        if rank == 0:
+            print(json.dumps(c4), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if args.workload != "vocoder":
         run_tts_workload(args, rank, local_rank, world, dev, dist)
         if dist is not None:

@@ -1029,9 +1029,10 @@ extern "C" int tb200_respair(const tb200_respair_params* p, void* stream_v) {
   if ((reinterpret_cast<uintptr_t>(p->y) & 15) || p->y_ld % unit_y || p->y_bs % unit_y || p->y_ld < (p->L_max + unit_y - 1) / unit_y * unit_y)
     return fail(TB200_E_BADARG, "respair: y must be 16-byte aligned with row pitch and batch stride multiples of %d elements", unit_y);
   if (p->x == p->y) return fail(TB200_E_BADARG, "respair: in-place operation is not supported (tiles read their neighbours' halos)");
+  // offsets are 64-bit across utterances; one utterance (C rows of the row pitch) must stay below 2^31 elements
   const long long lim = 1LL << 31;
-  if ((long long)p->B * p->x_bs >= lim || (long long)p->B * p->y_bs >= lim || p->x_bs < 0 || p->y_bs < 0)
-    return fail(TB200_E_BADARG, "respair: tensors must be addressable with 32-bit element offsets");
+  if ((long long)p->C * p->x_ld >= lim || (long long)p->C * p->y_ld >= lim || p->x_bs < 0 || p->y_bs < 0)
+    return fail(TB200_E_BADARG, "respair: one utterance (C x row pitch) must be below 2^31 elements, batch strides >= 0");
   PairDevice* d = nullptr;
   int rc = pair_device(d);
   if (rc) return rc;
@@ -1085,8 +1086,9 @@ extern "C" int tb200_conv1d_staged(const tb200_conv1d_params* p, void* stream_v)
     return fail(TB200_E_BADARG, "conv1d_staged: x, y and residual must be 16-byte aligned with 16-byte multiples as row pitch and batch stride");
   if (p->x == p->y) return fail(TB200_E_BADARG, "conv1d_staged: in-place operation is not supported (tiles read their neighbours' halos)");
   const long long lim = 1LL << 31;
-  if ((long long)p->B * p->x_bs >= lim || (long long)p->B * p->y_bs >= lim || (p->residual && (long long)p->B * p->r_bs >= lim))
-    return fail(TB200_E_BADARG, "conv1d_staged: tensors must be addressable with 32-bit element offsets");
+  if ((long long)p->C_in * p->x_ld >= lim || (long long)p->C_out * p->y_ld >= lim || (p->residual && (long long)p->C_out * p->r_ld >= lim) ||
+      p->x_bs < 0 || p->y_bs < 0 || (p->residual && p->r_bs < 0))
+    return fail(TB200_E_BADARG, "conv1d_staged: one utterance (C x row pitch) must be below 2^31 elements, batch strides >= 0");
   PairDevice* d = nullptr;
   int rc = pair_device(d);
   if (rc) return rc;

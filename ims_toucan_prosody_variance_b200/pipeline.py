@@ -15,7 +15,7 @@ SAMPLE_RATE = 24_000
 
 
 class TextToWave:
-    def __init__(self, phone2mel, mel2wav, max_batch=64, max_padding_ratio=1.5):
+    def __init__(self, phone2mel, mel2wav, max_batch=128, max_padding_ratio=None):
         self.phone2mel, self.mel2wav = phone2mel, mel2wav
         self.max_batch, self.max_padding_ratio = max_batch, max_padding_ratio
 
@@ -33,7 +33,7 @@ class TextToWave:
     @torch.no_grad()
     def synthesize(self, texts, utterance_embeddings, lang_ids=None, noise="device", device=None, **prosody):
         """texts: list of (T_i,62) tensors; utterance_embeddings: (N,E) or a single (E,) vector; lang_ids: (N,) or
-        int or None.  Utterances are bucketed by length (bounded padding) and synthesised batch by batch.
+        int or None.  Utterances are sorted by length and synthesised in batches of at most `max_batch`.
         Returns a list of N 1-D fp32 CUDA waveforms in input order."""
         n = len(texts)
         if n == 0:

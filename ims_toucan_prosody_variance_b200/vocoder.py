@@ -111,34 +111,70 @@ class _GeneratorBase(torch.nn.Module):
 
     # -- workspace ---------------------------------------------------------------------------
     def _workspace(self, b, frames, dev):
+        """Stage buffers for a (b, frames) batch, carved out of flat per-name allocations that only ever grow: a
+        different bucket shape re-uses the same memory without a fill (every kernel masks by the utterance lengths,
+        nothing is read unmasked past them -- tests/test_vocoder_gpu.py::test_workspace_garbage_is_never_read)."""
         key = (b, frames, str(dev))
         ws = self._buffers_cache.get(key)
         if ws is None:
-            self._buffers_cache.clear()
+            self._buffers_cache = {k: v for k, v in self._buffers_cache.items() if k == "flat"}
+            flat = self._buffers_cache.setdefault("flat", {})
+
+            def carve(name, shape, dtype):
+                need = shape[0] * shape[1] * shape[2]
+                buf = flat.get(name)
+                if buf is None or buf.numel() < need or buf.dtype != dtype or buf.device != dev:
+                    flat.pop(name, None)
+                    buf = flat[name] = torch.zeros(need, dtype=dtype, device=dev)
+                return buf[:need].view(shape)
+
             # residual stream: fp32 (default) or fp16 (activation_dtype="f16": halves the HBM bytes per element; every
             # value is rounded to 11 bits once more per layer -- measured SNR in tests/test_vocoder_gpu.py)
             sdt = torch.float16 if self.activation_dtype == "f16" else torch.float32
             pad = _pad8   # 16-byte aligned rows for either type (vector loads, bulk copies of tb200_respair)
-            ws = {"h": torch.zeros((b, self.channels, pad(frames)), dtype=sdt, device=dev)}
+            ws = {"h": carve("h", (b, self.channels, pad(frames)), sdt)}
             length = frames
             for i, u in enumerate(self.upsample_scales):
                 length *= u
                 c = self._stage_channels(i)
                 for name in ("up", "r0", "r1", "sum"):
-                    ws[f"{name}{i}"] = torch.zeros((b, c, pad(length)), dtype=sdt, device=dev)
+                    ws[f"{name}{i}"] = carve(f"{name}{i}", (b, c, pad(length)), sdt)
                 # value between the two convs of a residual pair: an MMA operand only -> fp16 in the
                 # fp16-operand mode, fp32 otherwise
                 tdt = torch.float16 if self.precision == "f16" else torch.float32
                 # row pitch a multiple of 8 elements: the lane=channel snake staging reads 16-byte groups
-                ws[f"t{i}"] = torch.zeros((b, c, _pad8(length) + 8), dtype=tdt, device=dev)
+                ws[f"t{i}"] = carve(f"t{i}", (b, c, _pad8(length) + 8), tdt)
             self._buffers_cache[key] = ws
         return ws
 
     # -- the generator -----------------------------------------------------------------------
+    # workspace bytes a single forward_batch call may take; larger batches run in chunks
+    max_workspace_bytes = 64 << 30
+
+    def _max_chunk(self, frames):
+        """Largest batch one kernel pass takes: every stage tensor must stay below 2^31 elements (the per-layer
+        epilogue's fast path uses 32-bit element offsets) and the workspace inside `max_workspace_bytes`."""
+        esz = 2 if self.activation_dtype == "f16" else 4
+        length, per_utt_elems, per_utt_bytes = frames, self.channels * _pad8(frames), self.channels * _pad8(frames) * esz
+        for i, u in enumerate(self.upsample_scales):
+            length *= u
+            n = self._stage_channels(i) * (_pad8(length) + 8)
+            per_utt_elems = max(per_utt_elems, n)
+            per_utt_bytes += n * (4 * esz + (2 if self.precision == "f16" else 4))
+        return max(1, min(((1 << 31) - 1) // per_utt_elems, self.max_workspace_bytes // per_utt_bytes))
+
     @torch.no_grad()
     def forward_batch(self, c, lengths=None):
         """c (B,80,F) fp32 CUDA; lengths (B) frames per utterance (int tensor) or None.
         Returns a new tensor wave (B, F*prod(scales)) fp32; samples past lengths[b]*384 are zero."""
+        b, _, frames = c.shape
+        cap = self._max_chunk(frames)
+        if b <= cap:
+            return self._forward_chunk(c, lengths)
+        parts = [self._forward_chunk(c[i:i + cap], None if lengths is None else lengths[i:i + cap]) for i in range(0, b, cap)]
+        return torch.cat(parts, dim=0)
+
+    def _forward_chunk(self, c, lengths=None):
         if self._packed is None:
             self.remove_weight_norm()
         pk = self._packed

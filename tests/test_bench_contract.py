@@ -12,7 +12,7 @@ BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_bench_line_has_every_contract_key():
-    with open(os.path.join(ROOT, "profiles", "r1_bench_line_bigvgan.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r2_bench_line_bigvgan.json")) as f:
         d = json.loads(f.read())
     for k in BASE_KEYS + ["clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]:
         assert k in d, k

@@ -116,6 +116,39 @@ def test_snake_pair_large_alpha(cuda):
     _run(cuda, B=1, C=32, K=3, dil=1, L=600, snake=True, alpha_scale=1.5, seed=9, tol=4e-3)
 
 
+@pytest.mark.parametrize("snake", [False, True])
+def test_pair_batch_stride_beyond_32_bits(cuda, snake):
+    """Utterances more than 2^31 elements apart (a 256-utterance text->wave bucket at the C = 32 stage is 3.1 G elements):
+    offsets across utterances are 64-bit.  Two utterances placed 2^31 + 64 elements apart inside one 4.3 GB buffer must
+    give the same result as the same two utterances in a compact tensor."""
+    from ims_toucan_prosody_variance_b200 import ops
+    C, K, L = 32, 3, 1000
+    g = torch.Generator().manual_seed(3)
+    w1 = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
+    w2 = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
+    b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    act = (torch.randn(C, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3)
+    c1 = ops.ConvLayer(w1.to(cuda), b1.to(cuda), dilation=1, padding=1, precision="f16")
+    c2 = ops.ConvLayer(w2.to(cuda), b2.to(cuda), dilation=1, padding=1, precision="f16")
+    a = tuple(t.to(cuda) for t in act) if snake else None
+    pair = ops.ResPair(c1, c2, a, a)
+    x = torch.randn(2, C, L, generator=g).half().to(cuda)
+    lens = torch.tensor([L, 777], dtype=torch.int32, device=cuda)
+    y_ref = torch.zeros_like(x)
+    pair(x, lens, y_ref, l_max=L)
+    far = (1 << 31) + 64
+    xbuf = torch.zeros(far + C * L, dtype=torch.float16, device=cuda)
+    ybuf = torch.zeros(far + C * L, dtype=torch.float16, device=cuda)
+    xs = xbuf.as_strided((2, C, L), (far, L, 1))
+    ys = ybuf.as_strided((2, C, L), (far, L, 1))
+    xs.copy_(x)
+    pair(xs, lens, ys, l_max=L)
+    torch.cuda.synchronize()
+    assert torch.equal(ys, y_ref)
+    del xbuf, ybuf
+    torch.cuda.empty_cache()
+
+
 def test_pair_rejects_unsupported(cuda):
     from ims_toucan_prosody_variance_b200 import ops
     from ims_toucan_prosody_variance_b200._lib import EngineError

@@ -36,6 +36,11 @@ def test_bucket_by_length_bounds_padding():
         assert len(b) <= 16
         assert max(lens[i] for i in b) <= 1.25 * min(lens[i] for i in b)
     assert sharding.bucket_by_length([], lens, 4) == []
+    # default policy: no ratio bound -> length-sorted batches, all full except the last
+    batches = sharding.bucket_by_length(range(100), lens, max_batch=16)
+    assert [len(b) for b in batches] == [16] * 6 + [4]
+    flat = [lens[i] for b in batches for i in b]
+    assert flat == sorted(lens, reverse=True)
 
 
 def _free_port():

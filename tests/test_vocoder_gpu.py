@@ -158,3 +158,36 @@ def test_fp16_residual_stream_mode(cuda, tmp_path, kind):
         snr = restate.snr_db(wave[b, :n * 384], fwd(fsd, mel[b, :, :n]))
         print(f"{kind} fp16 residual stream, utterance {b}: SNR {snr:.1f} dB")
         assert snr >= 40.0, f"{kind} utterance {b}: SNR {snr:.1f} dB"
+
+
+@pytest.mark.parametrize("streams", ["f32", "f16"])
+@pytest.mark.parametrize("kind", ["hifigan", "bigvgan"])
+def test_workspace_garbage_is_never_read(cuda, tmp_path, kind, streams):
+    """The stage buffers are re-used across batches of different shapes without a fill: whatever a previous batch left
+    past an utterance's length (or in the row padding) must never reach a result.  Run a ragged batch on a clean
+    workspace, poison every workspace buffer (large finite values, then NaN), run again: bit-identical waveforms."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory
+    sd = factory.make_state_dict(kind, 1234)
+    path = os.path.join(tmp_path, f"{kind}_{streams}_ws.pt")
+    torch.save({"generator": sd}, path)
+    cls = tb.HiFiGANGenerator if kind == "hifigan" else tb.BigVGAN
+    model = cls(path, precision="f16", activation_dtype=streams).to(cuda)
+    model.remove_weight_norm()
+    lens = [45, 44, 19, 2, 1, 0, 33]
+    mel = factory.make_mel(len(lens), max(lens), seed=21).to(cuda)
+    lt = torch.tensor(lens)
+    clean = model.forward_batch(mel, lt).clone()
+    for poison in (3.0e4, -3.0e4, float("nan")):
+        for buf in model._buffers_cache["flat"].values():
+            buf.fill_(poison)
+        again = model.forward_batch(mel, lt)
+        torch.cuda.synchronize()
+        assert torch.equal(again, clean), f"{kind}/{streams}: workspace content ({poison}) leaked into the result"
+    # a longer batch first, then the short ragged one in the same (larger) allocation
+    big = factory.make_mel(3, 64, seed=22).to(cuda)
+    model.forward_batch(big, torch.tensor([64, 50, 64]))
+    again = model.forward_batch(mel, lt)
+    assert torch.equal(again, clean)
+    for b, n in enumerate(lens):
+        assert torch.all(again[b, n * 384:] == 0)
