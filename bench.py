@@ -336,6 +336,8 @@ def run_config4(args, rank, world, dev, dist):
     mine = shards[rank]
     tts = tb.ToucanTTS(weights=factory.make_state_dict("toucantts", 1234), precision=args.acoustic_precision).to(dev)
     tts.store_inverse_all()
+    if not args.config4_no_graphs:
+        tts.enable_cuda_graphs()       # both acoustic segments replayed per padded batch shape (captured by the warm-up pass)
     voc, _ = build_generator(args.vocoder, args.precision, dev, args.activations)
     kw = {}
     if args.config4_max_batch:
@@ -379,7 +381,8 @@ def run_config4(args, rank, world, dev, dist):
     total_audio = float(audios.sum())
     assert int((all_len > 0).sum()) == n_total and abs(float(all_len.sum()) / SAMPLE_RATE - total_audio) < 1e-6 * total_audio + 1e-3
     return {"workload": f"text->wave, ONE global batch of {n_total} ragged utterances (20..200 phonemes) partitioned by utterance "
-                        f"(LPT on estimated cost) over {world} GPU(s), ToucanTTS ({args.acoustic_precision}) + {args.vocoder}",
+                        f"(LPT on estimated cost) over {world} GPU(s), ToucanTTS ({args.acoustic_precision}"
+                        f"{'' if args.config4_no_graphs else ', CUDA-graph replay per batch shape'}) + {args.vocoder}",
             "scaling": "strong", "utterances": n_total, "audio_s": round(total_audio, 2), "ms": round(t_max, 3),
             "value": round(total_audio / (t_max / 1e3), 2), "unit": UNIT, "rank_ms_max": round(t_max, 3),
             "rank_ms_mean": round(t_mean, 3), "imbalance": round(t_max / t_mean - 1.0, 4),
@@ -406,6 +409,7 @@ def main():
     ap.add_argument("--config4-max-batch", type=int, default=None, help="TextToWave bucket size (default: the engine's)")
     ap.add_argument("--config4-padding-ratio", type=float, default=None, help="TextToWave longest/shortest ratio per bucket")
     ap.add_argument("--config4-only", action="store_true", help="debug: print only the config4 object")
+    ap.add_argument("--config4-no-graphs", action="store_true", help="acoustic model launched eagerly instead of CUDA-graph replay")
     args = ap.parse_args()
     args.batch_given = args.batch is not None
     if args.batch is None:

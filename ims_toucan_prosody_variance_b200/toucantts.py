@@ -86,6 +86,7 @@ class ToucanTTS(torch.nn.Module):
         layouts.attach(self, lay, alias)
         self._packed = None
         self._pos_cache = {}
+        self._graphs = None          # enable_cuda_graphs()
         if weights is not None:
             self.load_state_dict(weights)
         self.eval()
@@ -101,6 +102,8 @@ class ToucanTTS(torch.nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise EngineError("toucan_b200 ToucanTTS runs on CUDA only: call .to('cuda') before store_inverse_all()/forward()")
+        if self._graphs is not None:
+            self._graphs = {}        # captured graphs point into the previous packing
         # folded on the host (load time; a few hundred small tensors), so that the only device work of loading a model is
         # the packing kernels of this library and plain copies
         sd = {k: v.to(dev) for k, v in layouts.fold_weight_norm({k: v.detach().cpu() for k, v in self.state_dict().items()}).items()}
@@ -145,7 +148,7 @@ class ToucanTTS(torch.nn.Module):
             blk.bn = tuple(f32(sd[f"{p}conv_module.norm.{n}"]) for n in ("running_mean", "running_var", "weight", "bias"))
             blk.norms = {n: (f32(sd[f"{p}{n}.weight"]), f32(sd[f"{p}{n}.bias"]))
                          for n in ("norm_ff_macaron", "norm_mha", "norm_conv", "norm_ff", "norm_final")}
-            blk.pos_table = None
+            blk.pos_table, blk.pos16, blk.pos_tables = None, None, {}
             return blk
 
         pk["enc"] = [block(f"encoder.encoders.{i}.") for i in range(self.encoder_layers)]
@@ -213,11 +216,14 @@ class ToucanTTS(torch.nn.Module):
     # relative positional table (PositionalEncoding.py:95-130) and its per-layer projection
     # ------------------------------------------------------------------------------------------
     def _positions(self, blk, l_max, dev):
-        """(D, 2*cap-1) tensor whose column (cap-1-r) holds linear_pos(PE(r)); cached per layer."""
+        """(D, 2*cap-1) tensor whose column (cap-1-r) holds linear_pos(PE(r)); computed once per layer and table size
+        and kept for the model's lifetime (captured CUDA graphs hold pointers into these tables)."""
         cap = 256
         while cap < l_max:
             cap *= 2
-        if blk.pos_table is not None and blk.pos_table[1] == cap:
+        hit = blk.pos_tables.get((cap, str(dev)))
+        if hit is not None:
+            blk.pos_table, blk.pos16 = hit
             return blk.pos_table
         key = (cap, str(dev))
         pe = self._pos_cache.get(key)
@@ -234,8 +240,10 @@ class ToucanTTS(torch.nn.Module):
         out = torch.zeros((1, self.attention_dimension, pe.shape[2]), dtype=torch.float32, device=dev)
         blk.pos(pe, None, out, l_in_max=2 * cap - 1)
         blk.pos_table = (out[0], cap)
+        blk.pos16 = None
         if self.precision != "fp32":   # operand rows of the tensor-core attention, packed once per layer and table size
             blk.pos16 = ops.pack_relpos_table(out[0][:, :2 * cap - 1], cap - 1, self.attention_heads)
+        blk.pos_tables[(cap, str(dev))] = (blk.pos_table, blk.pos16)
         return blk.pos_table
 
     # ------------------------------------------------------------------------------------------
@@ -308,35 +316,89 @@ class ToucanTTS(torch.nn.Module):
         in utterance order); "device" -> drawn on the GPU; or a (B,80,>=Fmax) tensor of standard normals.
         Returns a dict: mel_ncl (B,80,F'max_ld), mel_lengths (B) int32 [= 2*floor(F/2)], frames (B) int32,
         decoded_ncl (B,80,Fld), durations (B,T) int64, pitch (B,T), energy (B,T), log_durations (B,T) or None.
-        taps: optional dict that receives clones of the stage outputs (NCL) for per-stage parity checks."""
+        taps: optional dict that receives clones of the stage outputs (NCL) for per-stage parity checks.
+
+        The path is two device-only segments around its one host sync (the frame counts that size the decoder
+        buffers): `_segment_text` (encoder, predictors, prosody edits) and `_segment_frames` (length regulator,
+        decoder, PostNet, PostFlow).  With `enable_cuda_graphs()` each segment is captured once per padded shape and
+        replayed (see `_graphed`)."""
         if self._packed is None:
             self.store_inverse_all()
-        pk = self._packed
         dev = text_tensors.device
         if dev.type != "cuda":
             raise EngineError("toucan_b200 has no CPU path: tensors must live on a CUDA device")
-        b, t_max, idim = text_tensors.shape
-        d = self.attention_dimension
+        b, t_max, _ = text_tensors.shape
+        odim = self.output_spectrogram_channels
         text = text_tensors.contiguous().float()
         tlen = text_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        if self.multispeaker_model and utterance_embedding is None:
+            raise EngineError("multispeaker model needs an utterance embedding")
+        emb = utterance_embedding.to(dev).reshape(b, -1).float().contiguous() if self.multispeaker_model else None
+        lang = lang_ids.to(dev).reshape(-1).long() if (self.multilingual_model and lang_ids is not None) else None
+        scal = (float(duration_scaling_factor), float(pitch_variance_scale), float(energy_variance_scale),
+                float(pause_duration_scaling_factor))
+        graphs = (self._graphs is not None and taps is None and gold_durations is None and gold_pitch is None
+                  and gold_energy is None)
+
+        if graphs:
+            r1, key1 = self._graphed_text(text, tlen, emb, lang, scal)
+        else:
+            gold = tuple(None if g is None else g.to(dev) for g in (gold_durations, gold_pitch, gold_energy))
+            r1 = self._segment_text(text, tlen, emb, lang, gold, scal, t_max, taps)
+
+        # ---- the one host sync of the path: frame counts size every later buffer
+        frames_host = r1["frames"].cpu()
+        f_max = int(frames_host.max())
+        if f_max <= 0:
+            raise EngineError("synthesize_batch: no frames to synthesise")
+        if f_max // 2 <= 0:
+            raise EngineError("synthesize_batch: utterances shorter than 2 frames cannot pass the PostFlow")
+        f_run = (f_max + 63) // 64 * 64 if graphs else f_max      # graphs: one capture per 64-frame bucket
+        f_ld = _pad4(f_run)
+        if noise is None:
+            zn = torch.zeros((b, odim, f_ld), dtype=torch.float32)
+            for i in range(b):
+                fi = int(frames_host[i])
+                if fi > 0:
+                    zn[i, :, :fi] = torch.randn((1, odim, fi))[0]
+            zn = zn.to(dev)
+        elif isinstance(noise, str) and noise == "device":
+            zn = torch.randn((b, odim, f_ld), dtype=torch.float32, device=dev)
+        else:
+            zn = torch.zeros((b, odim, f_ld), dtype=torch.float32, device=dev)
+            zn[:, :, :f_max] = noise.to(dev)[:, :, :f_max]
+
+        if graphs:
+            r2 = self._graphed_frames(key1, r1, tlen, zn, f_run)
+        else:
+            r2 = self._segment_frames(r1["enc"], r1["cum"], tlen, r1["frames"], r1["pitch"], r1["energy"], zn, f_run, taps)
+        return dict(mel_ncl=r2["mel"], mel_lengths=r2["mel_lengths"], frames=r1["frames"], decoded_ncl=r2["decoded"],
+                    durations=r1["dur"], pitch=r1["pitch"], energy=r1["energy"], log_durations=r1["log_d"],
+                    frames_host=frames_host)
+
+    def _segment_text(self, text, tlen, emb, lang, gold, scal, t_max, taps=None):
+        """Encoder, variance predictors, prosody edits, duration rounding + prefix sums (A2-A8).  Device only.
+        text (B,T,62) with T >= t_max; every kernel masks by tlen, so t_max may be padded up."""
+        pk = self._packed
+        dev = text.device
+        b, _, idim = text.shape
+        d = self.attention_dimension
+        duration_scale, pitch_scale, energy_scale, pause_scale = scal
+        gold_durations, gold_pitch, gold_energy = gold
         t_ld = _pad4(t_max)
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
 
         # ---- utterance embedding: normalised once here (InferenceToucanTTS.py:202), once more in the encoder (Conformer.py:132)
         e1 = e2 = None
         if self.multispeaker_model:
-            if utterance_embedding is None:
-                raise EngineError("multispeaker model needs an utterance embedding")
-            e1 = ops.l2_normalize(utterance_embedding.to(dev).reshape(b, -1))
+            e1 = ops.l2_normalize(emb)
             e2 = ops.l2_normalize(e1)
 
         # ---- encoder (Conformer.py:92-134)
         x_in = ops.to_ncl(text, tlen, z(b, idim, t_ld), t_max)
         h100 = pk["embed0"](x_in, tlen, z(b, pk["embed0"].c_out, t_ld), l_in_max=t_max, out_act=OUT_TANH)
         x = pk["embed2"](h100, tlen, z(b, d, t_ld), l_in_max=t_max)
-        lang_vec = None
-        if self.multilingual_model and lang_ids is not None:
-            lang_vec = pk["lang_emb"].index_select(0, lang_ids.to(dev).reshape(-1).long()).contiguous()
+        lang_vec = pk["lang_emb"].index_select(0, lang).contiguous() if lang is not None else None
         ops.rowvec_affine(x, tlen, x, t_max, vec=lang_vec, scale=math.sqrt(d))
         ws = self._conformer_ws(b, t_max, self.encoder_units, dev)
         for blk in pk["enc"]:
@@ -357,36 +419,41 @@ class ToucanTTS(torch.nn.Module):
             pitch = self._predictor("pitch", enc, tlen, t_max, cln, base["pitch"])
         else:
             pitch = z(b, t_ld)
-            pitch[:, :t_max] = gold_pitch.to(dev).reshape(b, t_max).float()
+            pitch[:, :t_max] = gold_pitch.reshape(b, t_max).float()
         if gold_energy is None:
             energy = self._predictor("energy", enc, tlen, t_max, cln, base["energy"])
         else:
             energy = z(b, t_ld)
-            energy[:, :t_max] = gold_energy.to(dev).reshape(b, t_max).float()
+            energy[:, :t_max] = gold_energy.reshape(b, t_max).float()
         log_d = None
         if gold_durations is None:
             log_d = self._predictor("duration", enc, tlen, t_max, cln, base["duration"])
-            dur, cum, frames = ops.duration_finalize(text, tlen, log_dur=log_d, pause_scale=pause_duration_scaling_factor,
-                                                     duration_scale=duration_scaling_factor)
+            dur, cum, frames = ops.duration_finalize(text, tlen, log_dur=log_d, pause_scale=pause_scale,
+                                                     duration_scale=duration_scale)
         else:
             gd = torch.zeros((b, t_ld), dtype=torch.int64, device=dev)
-            gd[:, :t_max] = gold_durations.to(dev).reshape(b, t_max).long()
-            dur, cum, frames = ops.duration_finalize(text, tlen, gold_dur=gd, pause_scale=pause_duration_scaling_factor,
-                                                     duration_scale=duration_scaling_factor)
+            gd[:, :t_max] = gold_durations.reshape(b, t_max).long()
+            dur, cum, frames = ops.duration_finalize(text, tlen, gold_dur=gd, pause_scale=pause_scale,
+                                                     duration_scale=duration_scale)
         if taps is not None:
             taps.update(encoder=enc.clone(), pitch_raw=pitch.clone(), energy_raw=energy.clone())
         pitch = pitch.contiguous()
         energy = energy.contiguous()
-        ops.variance_edit(pitch, text, tlen, 0, pitch_variance_scale)
-        ops.variance_edit(energy, text, tlen, 1, energy_variance_scale)
+        ops.variance_edit(pitch, text, tlen, 0, pitch_scale)
+        ops.variance_edit(energy, text, tlen, 1, energy_scale)
+        return dict(enc=enc, pitch=pitch, energy=energy, dur=dur, cum=cum, frames=frames, log_d=log_d)
 
-        # ---- the one host sync of the path: frame counts size every later buffer
-        frames_host = frames.cpu()
-        f_max = int(frames_host.max())
-        if f_max <= 0:
-            raise EngineError("synthesize_batch: no frames to synthesise")
+    def _segment_frames(self, enc, cum, tlen, frames, pitch, energy, zn, f_max, taps=None):
+        """Length regulator, decoder, feat_out + PostNet, PostFlow (A9-A13).  Device only; f_max >= max(frames) (every
+        kernel masks by `frames`, so it may be padded up); zn (B,80,>=f_max) standard normals (scaled by 0.8 here, in
+        place)."""
+        pk = self._packed
+        dev = enc.device
+        b = enc.shape[0]
+        d = self.attention_dimension
         f_ld = _pad4(f_max)
         odim = self.output_spectrogram_channels
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
 
         # ---- length regulator + pitch/energy embedding (A9, A10) straight into the PostFlow conditioning buffer
         cat = z(b, odim + d, f_ld)             # rows [0,80): refined mel, rows [80,272): upsampled enriched encoding
@@ -422,22 +489,8 @@ class ToucanTTS(torch.nn.Module):
         # ---- PostFlow (A13): Glow.forward(infer=True), blocks in reverse
         hid = self.flow_hidden
         g = pk["g_proj"](cat, frames, z(b, hid, f_ld), l_in_max=f_max)
-        if noise is None:
-            zn = torch.zeros((b, odim, f_ld), dtype=torch.float32)
-            for i in range(b):
-                fi = int(frames_host[i])
-                if fi > 0:
-                    zn[i, :, :fi] = torch.randn((1, odim, fi))[0]
-            zn = zn.to(dev)
-        elif isinstance(noise, str) and noise == "device":
-            zn = torch.randn((b, odim, f_ld), dtype=torch.float32, device=dev)
-        else:
-            zn = z(b, odim, f_ld)
-            zn[:, :, :f_max] = noise.to(dev)[:, :, :f_max]
         len2 = torch.div(frames, 2, rounding_mode="floor").to(torch.int32)
         l2_max = f_max // 2
-        if l2_max <= 0:
-            raise EngineError("synthesize_batch: utterances shorter than 2 frames cannot pass the PostFlow")
         l2_ld = _pad4(l2_max)
         ops.rowvec_affine(zn, frames, zn, f_max, scale=0.8)
         xf = ops.squeeze2(zn, frames, z(b, 2 * odim, l2_ld), f_max)
@@ -458,8 +511,80 @@ class ToucanTTS(torch.nn.Module):
             if taps is not None:
                 taps.setdefault("flow_blocks", []).append(xf.clone())
         mel = ops.squeeze2(xf, len2, z(b, odim, _pad4(2 * l2_max)), l2_max, inverse=True)
-        return dict(mel_ncl=mel, mel_lengths=(len2 * 2).to(torch.int32), frames=frames, decoded_ncl=decoded, durations=dur,
-                    pitch=pitch, energy=energy, log_durations=log_d, frames_host=frames_host)
+        return dict(mel=mel, mel_lengths=(len2 * 2).to(torch.int32), decoded=decoded)
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the two segments (one capture per padded shape)
+    # ------------------------------------------------------------------------------------------
+    def enable_cuda_graphs(self, max_cached=8):
+        """Capture `_segment_text` per (batch, phonemes padded to 8, scaling factors) and `_segment_frames` per (that key,
+        frames padded to 64) in CUDA graphs and replay them: the ~550 launches of a batch are enqueued by two graph
+        launches instead of ~25 ms of host work, which is what bounds batches of fewer than ~100 utterances.  Inputs
+        are copied into the graph's static buffers; results are views of graph-owned memory, valid until the next
+        call with the same shape (TextToWave consumes them immediately).  Padding is free: every kernel masks by the
+        utterance lengths.  `max_cached` bounds the captured text-segment shapes (LRU; their frame-segment graphs go
+        with them).  Eager execution stays the default and is what gold prosody inputs and `taps` use."""
+        self._graphs = {}
+        self._graphs_max = int(max_cached)
+
+    def disable_cuda_graphs(self):
+        self._graphs = None
+
+    @staticmethod
+    def _capture(fn):
+        """Warm `fn` up on a side stream (planner caches, position tables, allocator pool), then capture it."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
+        return graph, out
+
+    def _graphed_text(self, text, tlen, emb, lang, scal):
+        b, t_max, idim = text.shape
+        t_run = (t_max + 7) // 8 * 8
+        key = (b, t_run, emb is not None, lang is not None, scal, str(text.device))
+        ent = self._graphs.pop(key, None)
+        if ent is None:
+            while len(self._graphs) >= self._graphs_max:
+                self._graphs.pop(next(iter(self._graphs)))          # least recently used first
+            st = dict(text=torch.zeros((b, t_run, idim), dtype=torch.float32, device=text.device),
+                      tlen=torch.zeros_like(tlen), emb=None if emb is None else torch.zeros_like(emb),
+                      lang=None if lang is None else torch.zeros_like(lang))
+            ent = dict(static=st, frames={})
+        self._graphs[key] = ent                                       # most recently used last
+        st = ent["static"]
+        st["text"][:, :t_max].copy_(text)
+        st["tlen"].copy_(tlen)
+        if emb is not None:
+            st["emb"].copy_(emb)
+        if lang is not None:
+            st["lang"].copy_(lang)
+        if "graph" not in ent:
+            ent["graph"], ent["out"] = self._capture(
+                lambda: self._segment_text(st["text"], st["tlen"], st["emb"], st["lang"], (None, None, None), scal, t_run))
+        ent["graph"].replay()
+        return ent["out"], key
+
+    def _graphed_frames(self, key1, r1, tlen, zn, f_run):
+        ent1 = self._graphs[key1]
+        ent = ent1["frames"].get(f_run)
+        st = ent1["static"]
+        if ent is None:
+            if len(ent1["frames"]) >= 4:
+                ent1["frames"].pop(next(iter(ent1["frames"])))
+            zs = torch.zeros_like(zn)
+            ent = dict(zn=zs)
+            zs.copy_(zn)
+            ent["graph"], ent["out"] = self._capture(
+                lambda: self._segment_frames(r1["enc"], r1["cum"], st["tlen"], r1["frames"], r1["pitch"], r1["energy"], zs, f_run))
+            ent1["frames"][f_run] = ent
+        ent["zn"].copy_(zn)
+        ent["graph"].replay()
+        return ent["out"]
 
     # ------------------------------------------------------------------------------------------
     # reference-shaped entry points

@@ -288,3 +288,46 @@ def test_single_speaker_single_language_variant(cuda):
     assert torch.equal(r["durations"][0, :17].cpu(), ref["durations"])
     m = 2 * (frames // 2)
     assert _rel_l1(r["mel_ncl"][0, :, :m].t().cpu(), ref["mel"]) < 1e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_cuda_graph_replay_matches_eager(cuda, prec):
+    """enable_cuda_graphs(): both device segments are captured per padded shape (phonemes to 8, frames to 64) and
+    replayed.  Same inputs -> same integers and (padding only changes masked positions) the same mel as the eager path;
+    a second batch of the same shape re-uses the capture; a different shape captures anew; results of the eager path
+    are untouched by switching graphs on and off."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory
+    model = tb.ToucanTTS(weights=factory.make_state_dict("toucantts", 1234), precision=prec).to(cuda)
+    model.store_inverse_all()
+
+    def batch(lens, seed):
+        t = torch.zeros((len(lens), max(lens), 62))
+        for i, n in enumerate(lens):
+            t[i, :n] = factory.make_phoneme_tensor(n, seed + i)
+        emb = torch.stack([factory.make_utterance_embedding(seed + i) for i in range(len(lens))])
+        return t.to(cuda), torch.tensor(lens, dtype=torch.int32), emb.to(cuda), torch.full((len(lens),), 12)
+
+    def run(args, noise):
+        t, tl, emb, lang = args
+        r = model.synthesize_batch(t, tl, utterance_embedding=emb, lang_ids=lang, noise=noise)
+        torch.cuda.synchronize()
+        n = [int(v) for v in r["mel_lengths"].cpu()]
+        return ([r["mel_ncl"][i, :, :n[i]].clone() for i in range(len(n))], r["durations"][:, :t.shape[1]].clone(),
+                r["frames_host"].clone())
+
+    cases = [batch([29, 12, 5], 40), batch([27, 29, 3], 50), batch([41, 40], 60)]
+    noises = [torch.randn((len(c[1]), 80, 600), generator=torch.Generator().manual_seed(7 + i)) for i, c in enumerate(cases)]
+    eager = [run(c, n) for c, n in zip(cases, noises)]
+    model.enable_cuda_graphs(max_cached=2)
+    for rep in range(2):                      # second round: every shape is a replay (case 0 was evicted: LRU of 2 -> recapture)
+        for c, n, e in zip(cases, noises, eager):
+            mels, dur, frames = run(c, n)
+            assert torch.equal(frames, e[2]) and torch.equal(dur, e[1])
+            for got, ref in zip(mels, e[0]):
+                assert got.shape == ref.shape
+                assert _rel_l1(got.cpu(), ref.cpu()) < (1e-6 if prec == "fp32" else 1e-4)
+    assert len(model._graphs) == 2
+    model.disable_cuda_graphs()
+    mels, dur, frames = run(cases[0], noises[0])
+    assert all(torch.equal(a, b) for a, b in zip(mels, eager[0][0]))
