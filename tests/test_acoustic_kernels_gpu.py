@@ -152,10 +152,11 @@ def test_group_norm(cuda, c, groups, tanh, residual):
 # ---------------------------------------------------------------------------------------------
 # LayerNorm over channels / ConditionalLayerNorm (variance, not std, and no epsilon: reference quirk)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("c", [192, 256])
-def test_channel_norm_both_modes(cuda, c):
+@pytest.mark.parametrize("lens", [[257, 3, 64], [33, 5, 1], [1000, 999, 130, 65]])
+@pytest.mark.parametrize("c", [192, 256, 100])
+def test_channel_norm_both_modes(cuda, c, lens):
+    # C = 100 leaves part of the per-warp channel slots empty
     from ims_toucan_prosody_variance_b200 import ops
-    lens = [257, 3, 64]
     b, l_max = len(lens), max(lens)
     g = torch.Generator().manual_seed(c)
     x = torch.randn(b, c, l_max, generator=g) * 1.5 + 0.2
@@ -250,7 +251,13 @@ def test_squeeze2_roundtrip_and_layout(cuda):
 def test_cln_mlp(cuda):
     """All conditioning MLPs of the variance predictors in one launch: W4 tanh(W2 tanh(W0 e + b0) + b2) + b4."""
     from ims_toucan_prosody_variance_b200 import ops
-    n, b, e_dim, cc = 24, 5, 64, 256
+    _cln_case(cuda, 24, 5)
+    _cln_case(cuda, 3, 19)      # several utterance groups per MLP, the last one partial
+
+
+def _cln_case(cuda, n, b):
+    from ims_toucan_prosody_variance_b200 import ops
+    e_dim, cc = 64, 256
     g = torch.Generator().manual_seed(2)
     e = torch.randn(b, e_dim, generator=g)
     w0, b0 = torch.randn(n, e_dim, e_dim, generator=g) / 8, torch.randn(n, e_dim, generator=g) * 0.1
