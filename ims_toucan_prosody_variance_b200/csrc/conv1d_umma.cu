@@ -1201,6 +1201,12 @@ int conv1d_umma(const tb200_conv1d_params* p, cudaStream_t stream) {
   // pole: measured 30 K vs 8 K cycles per tile)
   a.n_prod = snake ? Roles<true>::kWorkers - 8
                    : Roles<false>::kWorkers - ((a.residual || a.accumulate || !(a.epi_fast || a.epi_up)) ? 8 : 4);
+  // The acoustic model's GEMMs (tf32 operands, or 1 x 1 convolutions over fp32 activations): 128-row tiles of 192-1536
+  // input channels staged through registers -- every producer task is one global-memory latency, the tile time is
+  // the staging time (traces: 33 K cycles per 128 x 128 panel with 6 producers, MMA issue 6 K, drain 11-17 K), so 10 + 4
+  // wins even with a residual in the epilogue: 1536->192 1.50 -> 0.97 ms, 384->1536 1.05 -> 0.68, 192->1536 0.92 -> 0.65,
+  // 192->192 0.134 -> 0.099 (128 x 866 / 433 positions; profiles/r2_nprod_pw.txt).
+  if (!snake && a.up == 0 && !a.x_f16 && (p->precision == TB200_PREC_TF32 || a.ntaps == 1)) a.n_prod = Roles<false>::kWorkers - 4;
   a.trace = nullptr;
   if (g_knobs.trace) {
     if (!g_trace) TB200_CUDA_CHECK(cudaMalloc(&g_trace, kTraceLen * sizeof(long long)));
