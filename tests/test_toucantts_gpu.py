@@ -331,3 +331,36 @@ def test_cuda_graph_replay_matches_eager(cuda, prec):
     model.disable_cuda_graphs()
     mels, dur, frames = run(cases[0], noises[0])
     assert all(torch.equal(a, b) for a, b in zip(mels, eager[0][0]))
+
+
+def test_duration_flip_rate_of_tensor_core_modes(cuda):
+    """Durations are round(exp(log_d) - 1) of the duration predictor's output.  The kernel that rounds is bit-exact,
+    but in the tf32 / f16 modes the encoder feeding the predictor runs on the tensor cores, so a log-duration that
+    lands within ~1e-3 of a rounding boundary can round the other way.  Measure how often, against the engine's own
+    fp32 mode (which matches the oracle's integers in every parity test): 96 utterances of 20..200 phonemes."""
+    import random
+
+    from oracle import factory
+    rng = random.Random(17)
+    lens = [rng.randint(20, 200) for _ in range(96)]
+    text = torch.zeros((len(lens), max(lens), 62))
+    for i, n in enumerate(lens):
+        text[i, :n] = factory.make_phoneme_tensor(n, 900 + i)
+    emb = torch.stack([factory.make_utterance_embedding(900 + i) for i in range(len(lens))])
+    tl = torch.tensor(lens, dtype=torch.int32)
+    lang = torch.full((len(lens),), 12)
+    durs = {}
+    for prec in ("fp32", "tf32", "f16"):
+        model, _ = _engine(cuda, prec)
+        r = model.synthesize_batch(text.to(cuda), tl, utterance_embedding=emb.to(cuda), lang_ids=lang, noise="device")
+        durs[prec] = torch.cat([r["durations"][i, :n].cpu() for i, n in enumerate(lens)])
+    total = durs["fp32"].numel()
+    lines = [f"== duration flips vs fp32 mode over {total} phonemes"]
+    for prec in ("tf32", "f16"):
+        diff = (durs[prec] - durs["fp32"]).abs()
+        flips = int((diff > 0).sum())
+        lines.append(f"{prec}: {flips} of {total} phonemes differ ({100.0 * flips / total:.3f} %), max |delta| {int(diff.max())} frame(s), "
+                     f"total frames {int(durs[prec].sum())} vs {int(durs['fp32'].sum())}")
+        assert int(diff.max()) <= 1, f"{prec}: a duration moved by more than one frame"
+        assert flips <= 0.01 * total, f"{prec}: {flips} of {total} durations flipped"
+    _log(lines)
