@@ -15,6 +15,7 @@ import wave as _wave
 import torch
 
 from ._lib import EngineError
+from .frontend import PhoneTensoriser
 from .pipeline import SAMPLE_RATE, TextToWave
 from .toucantts import ToucanTTS
 from .vocoder import BigVGAN, HiFiGANGenerator
@@ -55,6 +56,7 @@ class ToucanTTSInterface(torch.nn.Module):
                               "(the reference's MODELS_DIR shorthands need its model downloader)")
         self._frontend_factory = (lambda lang: text2phone) if text2phone is not None else _reference_frontend
         self._text2phone = text2phone
+        self._tensorisers = {}
         self._language = language
         checkpoint = torch.load(tts_model_path, map_location="cpu")
         self.use_lang_id = True
@@ -129,10 +131,30 @@ class ToucanTTSInterface(torch.nn.Module):
                                  pause_duration_scaling_factor=pause_duration_scaling_factor)
             return self.mel2wav(mel.transpose(0, 1))
 
+    def _tensorise(self, text_list, input_is_phones):
+        """Sentences -> list of (T_i, 62) feature tensors.  With the reference's frontend (anything that exposes its
+        `phone_to_vector` table) the character loop of string_to_tensor (TextFrontend.py:213-288) is replaced by the
+        vectorised lookup of frontend.PhoneTensoriser over all sentences at once, staged in pinned memory; the
+        grapheme-to-phoneme step stays the frontend's `get_phone_string`.  Other frontends: their own string_to_tensor."""
+        fe = self.text2phone
+        if hasattr(fe, "phone_to_vector") and (input_is_phones or hasattr(fe, "get_phone_string")):
+            tz = self._tensorisers.get(id(fe))
+            if tz is None:
+                try:
+                    tz = PhoneTensoriser.from_frontend(fe)
+                except ImportError:
+                    tz = False                     # no feature index available: keep the frontend's own loop
+                self._tensorisers = {id(fe): tz}
+            if tz:
+                strings = list(text_list) if input_is_phones else [
+                    fe.get_phone_string(text=t, include_eos_symbol=True, for_feature_extraction=True) for t in text_list]
+                return tz.batch(strings)[2]
+        return [fe.string_to_tensor(t, input_phonemes=input_is_phones) for t in text_list]
+
     def forward_batch(self, text_list, duration_scaling_factor=1.0, pitch_variance_scale=1.0, energy_variance_scale=1.0,
                       pause_duration_scaling_factor=1.0, input_is_phones=False, noise=None):
         """Additive batched entry: all sentences in one ragged engine call; returns a list of waveforms."""
-        phones = [self.text2phone.string_to_tensor(t, input_phonemes=input_is_phones) for t in text_list]
+        phones = self._tensorise(text_list, input_is_phones)
         return self.engine.synthesize(phones, self.default_utterance_embedding.cpu(),
                                       lang_ids=int(self.lang_id) if self.lang_id is not None else None, noise=noise,
                                       duration_scaling_factor=duration_scaling_factor, pitch_variance_scale=pitch_variance_scale,

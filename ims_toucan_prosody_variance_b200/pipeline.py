@@ -50,7 +50,8 @@ class TextToWave:
         out = [None] * n
         for batch in sharding.bucket_by_length(range(n), lengths, self.max_batch, self.max_padding_ratio):
             t_max = max(lengths[i] for i in batch)
-            x = torch.zeros((len(batch), t_max, texts[batch[0]].shape[1]), dtype=torch.float32)
+            # padded batch staged in pinned memory: the host-to-device copy below is asynchronous
+            x = torch.zeros((len(batch), t_max, texts[batch[0]].shape[1]), dtype=torch.float32, pin_memory=True)
             for row, i in enumerate(batch):
                 x[row, :lengths[i]] = texts[i]
             idx = torch.as_tensor(batch, dtype=torch.int64)

@@ -471,6 +471,38 @@ def bigvgan_forward(sd, mel, taps=None):
 # -----------------------------------------------------------------------------------------
 
 
+_PREVIOUS_PHONE_MODIFIERS = {
+    "\u02D0": "lengthened", "\u02D1": "half-length", "\u0306": "shortened", "\u0303": "nasal",
+    "\u02E5": "very-high-tone", "\u02E6": "high-tone", "\u02E7": "mid-tone", "\u02E8": "low-tone", "\u02E9": "very-low-tone",
+    "\u2B67": "rising-tone", "\u2B68": "falling-tone", "\u2B81": "peaking-tone", "\u2B83": "dipping-tone",
+}
+
+
+def string_to_tensor(phones, phone_to_vector, feature_to_index, handle_missing=True):
+    """Preprocessing/TextFrontend.py:213-288 with input_phonemes=True, character by character: primary stress marks
+    the next appended vector (:232-234, :282-284), 13 modifier characters set one feature of the previous vector
+    (:236-274), everything else is looked up (:276-280); an unknown character is skipped when handle_missing but
+    still resolves a pending stress mark (the `if stressed_flag` of :282 sits after the try / except)."""
+    phones = phones.replace("\u025A", "\u0259").replace("\u1D7B", "\u0268")          # :223
+    vectors = []
+    stressed = False
+    for char in phones:
+        if char == "\u02C8":
+            stressed = True
+        elif char in _PREVIOUS_PHONE_MODIFIERS:
+            vectors[-1][feature_to_index[_PREVIOUS_PHONE_MODIFIERS[char]]] = 1
+        else:
+            if handle_missing:
+                if char in phone_to_vector:
+                    vectors.append(list(phone_to_vector[char]))
+            else:
+                vectors.append(list(phone_to_vector[char]))
+            if stressed:
+                stressed = False
+                vectors[-1][feature_to_index["stressed"]] = 1
+    return torch.tensor(vectors, dtype=torch.float32).reshape(len(vectors), -1)
+
+
 def float2pcm(sig):
     """Utility/utils.py:20-33 (dtype int16): (sig * 32768).clip(-32768, 32767) truncated toward zero by astype."""
     import numpy as np

@@ -138,3 +138,35 @@ def test_cloner_override_path(cuda, tmp_path):
     text = factory.make_phoneme_tensor(15, 3)
     d[text[:, factory.FEAT_WORD_BOUNDARY] == 1] = 0
     assert out.shape[0] == 150 * 3 + 2 * (int(d.sum()) // 2) * 384
+
+
+def test_forward_batch_through_the_vectorised_tensoriser(cuda, tmp_path):
+    """A frontend that exposes the reference's `phone_to_vector` table (and a feature index) is tensorised by
+    frontend.PhoneTensoriser for the whole batch at once; the waveforms must equal those of the same frontend run
+    through its own per-sentence string_to_tensor loop (here the oracle's restatement of TextFrontend.py:213-288)."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import restate
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frontend.pt"))
+
+    class Loop:
+        def string_to_tensor(self, text, input_phonemes=False):
+            assert input_phonemes
+            return restate.string_to_tensor(text, gold["phone_to_vector"], gold["feature_to_index"])
+
+    class Vectorised(Loop):
+        phone_to_vector = gold["phone_to_vector"]
+        feature_to_index = gold["feature_to_index"]
+
+        def string_to_tensor(self, text, input_phonemes=False):
+            raise AssertionError("the batched path must not call the per-sentence loop")
+
+    tpath, vpath, _, _ = _models(cuda, tmp_path)
+    sentences = ["hˈɛloʊ wˈɜːld~#", "ðɪs ɪz ɐ tˈɛst.~#", "aː˥ b̃ˈa~#"]
+    results = []
+    for fe in (Loop(), Vectorised()):
+        tts = tb.ToucanTTSInterface(device="cuda", tts_model_path=tpath, vocoder_model_path=vpath, faster_vocoder=True,
+                                    language="en", text2phone=fe)
+        torch.manual_seed(3)
+        results.append(tts.forward_batch(sentences, input_is_phones=True))
+    for a, b in zip(*results):
+        assert a.numel() > 0 and torch.equal(a, b)
