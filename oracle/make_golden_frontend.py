@@ -42,7 +42,7 @@ def make_strings(keys, n, seed):
 
 
 def main():
-    shim.install()
+    shim.install(shim.FRONTEND_STUBS)
     from Preprocessing import TextFrontend
     from Preprocessing.articulatory_features import generate_feature_table, get_feature_to_index_lookup
 

@@ -43,29 +43,29 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "InferenceInterfaces"))
 
 
-_installed = False
+_installed = set()
+FRONTEND_STUBS = ["dragonmapper", "dragonmapper.transcriptions", "phonemizer", "phonemizer.backend", "pypinyin"]
 
 
-def install():
-    """Put the reference and the restated alias_free_torch on sys.path, register stubs."""
-    global _installed
-    if _installed:
-        return
+def install(stubs=None):
+    """Put the reference and the restated alias_free_torch on sys.path, register stubs (all of _STUBS by default; a
+    subset for callers that only need part of the reference -- a stubbed librosa in sys.modules changes what
+    third-party packages such as transformers believe is installed, so tests that do not need it do not register it)."""
     if not available():
         raise RuntimeError(f"live reference not found at {REFERENCE_ROOT} (it never exists on the GPU box)")
-    for name in _STUBS:
-        if name not in sys.modules:
+    for name in (_STUBS if stubs is None else stubs):
+        if name not in _installed and name not in sys.modules:
             try:
                 __import__(name)
             except Exception:
                 sys.modules[name] = _Stub(name)
+        _installed.add(name)
     here = os.path.dirname(os.path.abspath(__file__))
     if here not in sys.path:
         sys.path.insert(0, here)  # oracle/alias_free_torch wins over any installed one
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(1, REFERENCE_ROOT)
     warnings.filterwarnings("ignore", message=".*weight_norm.*")
-    _installed = True
 
 
 def reference_classes():
