@@ -877,7 +877,7 @@ struct PairDevice {
 };
 static PairDevice g_pair_dev[64];
 static long long* g_pair_trace = nullptr;
-static int g_pair_trace_on = -1, g_pair_debug = -1, g_pair_max_s = -1, g_pair_skip = 0;
+static int g_pair_trace_on = -1, g_pair_debug = -1, g_pair_max_s = -1, g_pair_skip = 0, g_pair_min_ring = 0;
 
 static int pair_device(PairDevice*& d) {
   int dev = 0;
@@ -895,6 +895,8 @@ static int pair_device(PairDevice*& d) {
     g_pair_max_s = e ? atoi(e) : 0;
     e = getenv("TB200_PAIR_SKIP");
     g_pair_skip = e ? atoi(e) : 0;
+    e = getenv("TB200_PAIR_MIN_RING");
+    g_pair_min_ring = e ? atoi(e) : 0;
   }
   return 0;
 }
@@ -960,7 +962,7 @@ static int plan_pair(PairArgs& a, bool snake, int smem_cap, int sm_count) {
       long long slots = avail / a.chunk_bytes;
       if (slots > 16) slots = 16;
       if (slots > nconv * a.n_chunks) slots = nconv * a.n_chunks;
-      if (slots < 3 || slots * a.chunk_bytes < 24 * 1024) continue;
+      if (slots < (g_pair_min_ring > 0 ? g_pair_min_ring : 3) || slots * a.chunk_bytes < 24 * 1024) continue;
       ring = (int)slots;
     }
     a.x_buf_bytes = x_buf; a.x_bufs = x_bufs;

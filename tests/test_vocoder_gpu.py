@@ -191,3 +191,28 @@ def test_workspace_garbage_is_never_read(cuda, tmp_path, kind, streams):
     assert torch.equal(again, clean)
     for b, n in enumerate(lens):
         assert torch.all(again[b, n * 384:] == 0)
+
+
+@pytest.mark.parametrize("kind", ["hifigan", "bigvgan"])
+def test_oversized_batches_run_in_chunks(cuda, tmp_path, kind):
+    """forward_batch splits a batch whose stage tensors would exceed 2^31 elements or the workspace budget; the chunked
+    result must equal the one-pass result (utterances are independent)."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory
+    sd = factory.make_state_dict(kind, 1234)
+    path = os.path.join(tmp_path, f"{kind}_chunk.pt")
+    torch.save({"generator": sd}, path)
+    cls = tb.HiFiGANGenerator if kind == "hifigan" else tb.BigVGAN
+    model = cls(path, precision="f16", activation_dtype="f16").to(cuda)
+    model.remove_weight_norm()
+    lens = [30, 29, 17, 30, 5, 22, 1]
+    mel = factory.make_mel(len(lens), max(lens), seed=31).to(cuda)
+    lt = torch.tensor(lens)
+    whole = model.forward_batch(mel, lt).clone()
+    assert model._max_chunk(max(lens)) >= len(lens)
+    model.max_workspace_bytes = 3 * (model.max_workspace_bytes // model._max_chunk(max(lens)) + 1)   # room for 2-3 utterances
+    cap = model._max_chunk(max(lens))
+    assert 1 <= cap < len(lens)
+    chunked = model.forward_batch(mel, lt)
+    assert chunked.shape == whole.shape and torch.equal(chunked, whole)
+    model.max_workspace_bytes = type(model).max_workspace_bytes
