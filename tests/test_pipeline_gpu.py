@@ -170,3 +170,28 @@ def test_forward_batch_through_the_vectorised_tensoriser(cuda, tmp_path):
         results.append(tts.forward_batch(sentences, input_is_phones=True))
     for a, b in zip(*results):
         assert a.numel() > 0 and torch.equal(a, b)
+
+
+def test_empty_and_one_phoneme_utterances_inside_a_batch(cuda, tmp_path):
+    """Ragged edge cases: an utterance of length 0 yields an empty waveform, a 1-phoneme utterance a short one, and
+    neither disturbs its neighbours (same waveforms as the batch without them)."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory
+    tpath, vpath, _, _ = _models(cuda, tmp_path)
+    tts = tb.ToucanTTS(weights=torch.load(tpath)["model"]).to(cuda)
+    tts.store_inverse_all()
+    voc = tb.HiFiGANGenerator(vpath).to(cuda)
+    voc.remove_weight_norm()
+    eng = tb.TextToWave(tts, voc)
+    texts = [factory.make_phoneme_tensor(14, 70), torch.zeros((0, 62)), factory.make_phoneme_tensor(1, 71),
+             factory.make_phoneme_tensor(9, 72)]
+    emb = torch.stack([factory.make_utterance_embedding(70 + i) for i in range(4)])
+    noise = torch.randn((4, 80, 400), generator=torch.Generator().manual_seed(8))
+    order = sorted(range(4), key=lambda i: (-texts[i].shape[0], i))                 # the batch is length-sorted inside
+    waves = eng.synthesize(texts, emb, lang_ids=12, noise=noise[order])
+    assert waves[1].numel() == 0
+    assert waves[2].numel() % 384 == 0 and torch.isfinite(waves[2]).all()
+    keep = [0, 3]
+    ref = eng.synthesize([texts[i] for i in keep], emb[keep], lang_ids=12, noise=noise[keep])
+    for i, r in zip(keep, ref):
+        assert waves[i].shape == r.shape and torch.allclose(waves[i], r, atol=2e-4), i
