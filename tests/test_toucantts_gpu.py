@@ -3,7 +3,7 @@ live reference, and batch-vs-single consistency.
 
 Tolerances (north_star): integer durations and frame counts bit-exact; mel relative L1 <= 1e-3 in the
 fp32-accumulate modes ("fp32" = CUDA-core fp32, "tf32" = tcgen05 kind::tf32 with fp32 accumulation in TMEM);
-the fp16-operand mode is the looser-bound mode (<= 1e-2)."""
+the fp16-operand mode (fp32 accumulation, the mantissa of tf32) is held to the same bound."""
 import os
 
 import pytest
@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MEL_TOL = {"fp32": 1e-3, "tf32": 1e-3, "f16": 1e-2}
+MEL_TOL = {"fp32": 1e-3, "tf32": 1e-3, "f16": 1e-3}   # fp16 operands carry tf32's mantissa: same bound (measured 2.0e-4)
 _ENGINES = {}
 
 
@@ -89,7 +89,7 @@ def test_stagewise_vs_oracle(cuda, prec):
         pytest.fail(f"{prec}: durations differ from the oracle's (see gpurun_out/toucantts_stage_errors.txt)")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
 def test_golden_fixture_cases(cuda, prec):
     """Outputs of the reference's unmodified InferenceToucanTTS (tests/golden/toucantts.pt, oracle/make_golden.py):
     predicted prosody, scaled prosody, external (cloner-shaped) prosody; noise from the global CPU generator."""
@@ -166,7 +166,7 @@ def test_long_form_external_prosody(cuda):
     assert torch.isfinite(mel).all()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
 def test_config3_length_mel_parity(cuda, prec):
     """BASELINE.json configs[2] at its longest utterance: 200 phonemes -> ~1 000 frames.  The decoder's attention then
     runs 16 key tiles per query tile and the k = 31 depthwise conv sees full-length rows; mel rel-L1 <= 1e-3 against the

@@ -10,7 +10,7 @@ python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; echo "exit $?" >> 
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?"
 python bench.py --vocoder hifigan --no-cpu-baseline --no-config4 > $out/${tag}_bench_hifigan.json 2>&1
 python bench.py --workload acoustic --steps 5 --no-config4 > $out/${tag}_bench_acoustic.json 2>&1
-python bench.py --workload acoustic --steps 5 --acoustic-precision f16 --no-cpu-baseline --no-config4 > $out/${tag}_bench_acoustic_f16.json 2>&1
+python bench.py --workload acoustic --steps 5 --acoustic-precision tf32 --no-cpu-baseline --no-config4 > $out/${tag}_bench_acoustic_tf32.json 2>&1
 python bench.py --workload e2e --steps 5 --no-config4 > $out/${tag}_bench_e2e.json 2>&1
 python bench.py --impl reference --steps 1 --warmup 0 > $out/${tag}_bench_ref.json 2>&1
 python tools/profile_vocoder.py bigvgan 64 500 f16 f16 > $out/${tag}_prof_bigvgan.log 2>&1
