@@ -79,7 +79,7 @@ def step_list(path, out):
     tot_ns = sum(d["gpu__time_duration.sum"] for d in per.values())
     rd = sum(d["dram__bytes_read.sum"] for d in per.values())
     wr = sum(d["dram__bytes_write.sum"] for d in per.values())
-    lines = [f"# ncu launch list of ONE timed BigVGAN step (bench.py --steps 1 --no-cpu-baseline; ncu -k regex:conv1d_umma -s 234 -c 78): {len(per)} launches",
+    lines = [f"# ncu launch list of ONE timed step of bench.py (tools/gpu_final.sh: -k regex of the conv kernels, -s warm-up launches, -c launches per step): {len(per)} launches",
              "# metrics: gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum (cold-cache, serialised: compare shares)",
              f"# total {tot_ns / 1e6:.3f} ms, DRAM read {rd / 1e9:.2f} GB, write {wr / 1e9:.2f} GB -> {(rd + wr) / len(per) / 1e6:.1f} MB per launch",
              f"{'#':>3s} {'kernel':44s} {'block':>13s} {'us':>10s} {'share':>6s} {'rd MB':>9s} {'wr MB':>9s}"]
