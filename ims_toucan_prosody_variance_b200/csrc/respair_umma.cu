@@ -247,11 +247,14 @@ __device__ __forceinline__ void pair_leaky_stage(const void* X, int PX, int tx0,
 // loops were 17 % of all executed instructions of a snake pair)
 // ---------------------------------------------------------------------------------------------
 // (__noinline__, loops not unrolled: one small copy each -- inlined at every wait site they were 3.5 K instructions)
+#ifndef TB200_PAIR_SLEEP_NS
+#define TB200_PAIR_SLEEP_NS 128
+#endif
 __device__ __noinline__ void pair_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
 #pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-    __nanosleep(128);
+    __nanosleep(TB200_PAIR_SLEEP_NS);
     if (mbar_try_wait(bar, parity)) return;
   }
   mbar_timeout();
