@@ -2,6 +2,7 @@
 without a GPU.  No compute calls here."""
 import ctypes
 import json
+import math
 import os
 import re
 
@@ -106,3 +107,32 @@ def test_fold_weight_norm_matches_torch():
     sd = {"c." + k: v.detach().clone() for k, v in conv.state_dict().items()}
     torch.nn.utils.remove_weight_norm(conv)
     assert torch.allclose(layouts.fold_weight_norm(sd)["c.weight"], conv.weight, atol=1e-6)
+
+
+def test_vocoder_chunk_limits(tmp_path):
+    """Host logic of forward_batch's chunking: a chunk keeps every stage tensor below 2^31 elements and the workspace
+    inside the budget; the configs of BASELINE.json run as one chunk."""
+    import ims_toucan_prosody_variance_b200 as tb
+    from oracle import factory
+    path = os.path.join(tmp_path, "b.pt")
+    torch.save({"generator": factory.make_state_dict("bigvgan", 7)}, path)
+    for streams, esz in (("f16", 2), ("f32", 4)):
+        m = tb.BigVGAN(path, activation_dtype=streams)
+        assert m._max_chunk(500) >= 64                       # config 2: 64 x 500 frames in one pass
+        for frames in (100, 500, 1000, 4000, 20000):
+            cap = m._max_chunk(frames)
+            assert cap >= 1
+            widest = max(m._stage_channels(i) * (frames * math.prod(m.upsample_scales[:i + 1]) + 16)
+                         for i in range(len(m.upsample_scales)))
+            assert cap * widest < (1 << 31) + widest          # per-stage element count of a chunk stays 32-bit addressable
+        small = type(m).max_workspace_bytes
+        m.max_workspace_bytes = 1 << 30
+        assert m._max_chunk(1000) < tb.BigVGAN(path, activation_dtype=streams)._max_chunk(1000)
+        m.max_workspace_bytes = small
+
+
+def test_text_to_wave_batches_are_length_sorted_groups():
+    from ims_toucan_prosody_variance_b200 import sharding
+    lens = [5, 200, 37, 37, 120, 1, 64]
+    batches = sharding.bucket_by_length(range(len(lens)), lens, max_batch=3)
+    assert batches == [[1, 4, 6], [2, 3, 0], [5]]
